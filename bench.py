@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched VE posterior queries (headline) + CPT-fit counting.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference-style CPU path (oracle port)
+
+Headline workload = BASELINE.json configs[1]: Asia (8 binary nodes), 1,048,576 evidence rows per GPU,
+evidence {asia, smoke, xray, dysp} drawn from the joint, targets lung / tub / bronc.  One *step* = the three
+compiled plans run over one batch of evidence rows; one *query* = one posterior row of one target.
+Inputs are device resident for `value`; `e2e` runs the same step through the C-ABI host-buffer call
+(pinned host codes in, pinned host posteriors out, copies inside the timed region).
+Between timed iterations the step rotates through a ring of distinct batches larger than L2.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ASIA_EVIDENCE = ["asia", "smoke", "xray", "dysp"]
+ASIA_TARGETS = ["lung", "tub", "bronc"]
+ROWS_PER_GPU = 1 << 20
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "posterior queries/sec (batched VE)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _profile_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            parts = [x.strip() for x in l.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_ve_queries_per_sec(budget_s, rows_per_call=65536, seed=11):
+    """The reference-style CPU path for a multi-layer network (oracle O2: textbook batched VE in
+    fp32 PyTorch on the host cores), on a bounded sample of the Asia workload.  Returns (queries/s, sample text, cores)."""
+    import numpy as np
+    import torch
+
+    from continuousbayesiannetwork_b200 import synth
+    from oracle import cbn_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = synth.asia()
+    n_fit = 200_000
+    codes = synth.sample_forward_numpy(spec, 1235, 0, n_fit)
+    fitted = [O.cpt_from_counts(O.dense_counts(codes, spec.parents[i] + [i], spec.cards), n_fit)[1] for i in range(spec.n)]
+    net = O.DiscreteNet(spec.cards, spec.parents, fitted)
+    ids = [spec.names.index(e) for e in ASIA_EVIDENCE]
+    ev = synth.sample_forward_numpy(spec, seed, 0, rows_per_call)[ids].T
+    O.ve_posterior(net, spec.names.index("lung"), ids, ev[:1024])           # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        for t in ASIA_TARGETS:
+            O.ve_posterior(net, spec.names.index(t), ids, ev)
+        done += rows_per_call * len(ASIA_TARGETS)
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return done / el, f"{done} queries = {done // (rows_per_call * 3)} x ({rows_per_call} rows x 3 targets) of the Asia workload in {el:.1f}s", torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 262144
+    import numpy as np
+    import torch
+
+    from continuousbayesiannetwork_b200 import synth
+    from oracle import cbn_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = synth.asia()
+    n_fit = 200_000
+    codes = synth.sample_forward_numpy(spec, 1235, 0, n_fit)
+    fitted = [O.cpt_from_counts(O.dense_counts(codes, spec.parents[i] + [i], spec.cards), n_fit)[1] for i in range(spec.n)]
+    net = O.DiscreteNet(spec.cards, spec.parents, fitted)
+    ids = [spec.names.index(e) for e in ASIA_EVIDENCE]
+    ev = synth.sample_forward_numpy(spec, 11, 0, rows)[ids].T
+
+    def step():
+        for t in ASIA_TARGETS:
+            O.ve_posterior(net, spec.names.index(t), ids, ev)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    q = rows * len(ASIA_TARGETS) * args.steps
+    val = q / el
+    sample = f"each step = {rows} evidence rows x 3 targets of the Asia workload (bounded sample of the 1,048,576-row batch)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "asia-8node, evidence {asia,smoke,xray,dysp}, targets lung/tub/bronc (BASELINE.json configs[1])",
+                   "rows_per_step": rows, "path": "reference-style PyTorch CPU path: oracle O2 textbook batched VE fp32 "
+                   "(the reference has no correct multi-layer query path, SURVEY.md 3.3)"},
+        "cpu_baseline": {"value": val, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from continuousbayesiannetwork_b200 import sharding, synth
+    from continuousbayesiannetwork_b200.engine import bind_inference, sample_network, tables_from_spec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak_gbs, peak_src = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        """W untimed steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launch
+        stream; MAX over ranks.  Returns seconds."""
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms) / 1e3
+
+    # ---------------- fit (config 2 shape): 1e7 forward samples sharded over the ranks, one int64 all-reduce
+    spec = synth.asia()
+    n_fit = 10_000_000
+    s, e = sharding.shard_range(n_fit, rank, world)
+    tables = tables_from_spec(spec, dev)
+    fit_codes = sample_network(spec, seed=1235, first=s, n=e - s, device=dev, tables=tables)
+    torch.cuda.synchronize()
+
+    def fit_step(_i):
+        tables.counts.zero_()
+        tables.n_total = 0
+        sharding.fit_sharded(tables, fit_codes, e - s)
+
+    fit_s = timed(fit_step, max(3, min(args.steps, 20)), 3)
+    fit_steps = max(3, min(args.steps, 20))
+    fit_rate = n_fit * fit_steps / fit_s
+    infer = bind_inference(tables)
+
+    # ---------------- queries: ring of distinct batches larger than L2
+    rows = args.rows
+    ld = (rows + 15) // 16 * 16
+    bytes_per_batch = len(ASIA_EVIDENCE) * ld + len(ASIA_TARGETS) * rows * 2 * 4
+    ring = max(2, -(-2 * L2_BYTES // bytes_per_batch))
+    ids = [spec.names.index(x) for x in ASIA_EVIDENCE]
+    ev_ring, out_ring = [], []
+    for r in range(ring):
+        # evidence rows drawn from the joint: forward samples with a per-rank, per-batch counter range
+        full = sample_network(spec, seed=4321, first=(rank * ring + r) * rows, n=rows, device=dev, tables=tables)
+        ev_ring.append(full[ids].contiguous())
+        out_ring.append([torch.empty((rows, 2), dtype=torch.float32, device=dev) for _ in ASIA_TARGETS])
+    del full
+    t_compile = time.perf_counter()
+    plans = [infer.plan(t, ASIA_EVIDENCE) for t in ASIA_TARGETS]
+    torch.cuda.synchronize()
+    compile_ms = (time.perf_counter() - t_compile) * 1e3
+
+    def query_step(i):
+        r = i % ring
+        for p, o in zip(plans, out_ring[r]):
+            p.run_codes(ev_ring[r], rows, out=o)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    q_s = timed(query_step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    queries_per_step = rows * len(ASIA_TARGETS) * world
+    value = queries_per_step * args.steps / q_s
+    launches = len(ASIA_TARGETS) * args.steps * world
+    # roofline of the dominant kernel (gather): algorithmic bytes = relevant evidence codes in + fp32 posterior out
+    alg_bytes = rows * plans[0].algorithmic_bytes_per_row()
+    launch_s = q_s / (len(ASIA_TARGETS) * args.steps)
+    achieved = alg_bytes / launch_s / 1e9
+
+    # ---------------- e2e through the C-ABI host-buffer call (pinned host memory in and out)
+    host_ev = [x.cpu().pin_memory() for x in ev_ring[:2]]
+    host_out = [[torch.empty((rows, 2), dtype=torch.float32).pin_memory() for _ in ASIA_TARGETS] for _ in range(2)]
+
+    def e2e_step(i):
+        r = i % 2
+        for p, o in zip(plans, host_out[r]):
+            p.run_codes_host(host_ev[r], rows, o)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = queries_per_step * e2e_steps / e2e_s
+    # parity spot check of what the e2e call returned against the device path
+    assert torch.equal(host_out[0][0], out_ring[0][0].cpu()) or args.steps < 1
+
+    # ---------------- e2e through the reference-facing Python API: infer(target, {name: float tensor [nq,1]})
+    f_ev = {nm: host_ev[0][k, :rows].to(torch.float32).reshape(-1, 1).pin_memory() for k, nm in enumerate(ASIA_EVIDENCE)}
+
+    def api_step(_i):
+        res = []
+        for tname in ASIA_TARGETS:
+            res.append(infer.infer(tname, f_ev).cpu())
+        return res
+
+    api_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    api_steps = 5
+    for i in range(api_steps):
+        api_step(i)
+    torch.cuda.synchronize()
+    api_s = max_over_ranks(time.perf_counter() - t0)
+    api_value = queries_per_step * api_steps / api_s
+
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, dev, rank, world, timed, peak_gbs)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sample, cores = cpu_ve_queries_per_sec(args.cpu_budget_s)
+            cpu = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": q_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "asia-8node batched VE, evidence {asia,smoke,xray,dysp}, targets lung/tub/bronc "
+                                   "(BASELINE.json configs[1])",
+                       "rows_per_gpu_per_step": rows, "queries_per_step": queries_per_step,
+                       "cpts": f"fitted on the GPU from {n_fit} forward samples (count kernel + int64 all-reduce)",
+                       "l2": f"ring of {ring} distinct batches, {ring * bytes_per_batch / 1e6:.0f} MB > 2 x 126 MB L2",
+                       "plan_compile_ms": compile_ms},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": len(ASIA_TARGETS) * len(ASIA_EVIDENCE) * rows * world,
+                    "d2h_bytes_per_step": len(ASIA_TARGETS) * rows * 2 * 4 * world,
+                    "call": "cbn_ve_run_codes_host (pinned host uint8 codes in, pinned host fp32 posteriors out)",
+                    "python_api": {"value": api_value, "unit": "queries/s",
+                                   "call": "ExactInference.infer(target, {name: pinned float32 [nq,1]}) -> .cpu()"}},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": _profile_traffic("gather_codes_kernel<2>"), "kernel": "gather_codes_kernel<2>",
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "fit": {"metric": "CPT-fit samples/sec", "value": fit_rate, "unit": "samples/s", "n_samples": n_fit,
+                    "n_vars": spec.n, "achieved_GBs": fit_rate * spec.n / 1e9, "frac_of_hbm_peak": fit_rate * spec.n / 1e9 / peak_gbs,
+                    "includes": "count kernel + int64 all-reduce + CPT normalisation"},
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(args, dev, rank, world, timed, peak_gbs):
+    """Other BASELINE.json configurations, reported beside the headline (not the bench value)."""
+    import torch
+
+    from continuousbayesiannetwork_b200 import sharding, synth
+    from continuousbayesiannetwork_b200.engine import install_cpts, sample_network, tables_from_spec
+
+    out = {}
+    # config 3: Alarm-shaped, 16M evidence rows sharded over the ranks (strong scaling inside this extra)
+    spec = synth.alarm()
+    tables, infer = install_cpts(spec, dev)
+    total_rows = 1 << 24
+    s, e = sharding.shard_range(total_rows, rank, world)
+    rows = e - s
+    ids = [spec.names.index(x) for x in synth.ALARM_EVIDENCE]
+    full = sample_network(spec, seed=777, first=s, n=rows, device=dev, tables=tables)
+    ev = full[ids].contiguous()
+    del full
+    t0 = time.perf_counter()
+    plans = [infer.plan(t, synth.ALARM_EVIDENCE) for t in synth.ALARM_TARGETS]
+    torch.cuda.synchronize()
+    compile_ms = (time.perf_counter() - t0) * 1e3
+    outs = [torch.empty((rows, p.card_t), dtype=torch.float32, device=dev) for p in plans]
+
+    def step(_i):
+        for p, o in zip(plans, outs):
+            p.run_codes(ev, rows, out=o)
+
+    k = max(3, min(args.steps, 10))
+    sec = timed(step, k, 3)
+    alg = sum(rows * p.algorithmic_bytes_per_row() for p in plans) * world
+    out["alarm"] = {"metric": METRIC, "value": total_rows * len(plans) * k / sec, "unit": "queries/s",
+                    "rows_total": total_rows, "targets": len(plans), "achieved_GBs": alg * k / sec / 1e9,
+                    "frac_of_hbm_peak": alg * k / sec / 1e9 / (peak_gbs * world), "plan_compile_ms": compile_ms,
+                    "table_cells": [p.stats.final_tables[0][1] for p in plans]}
+    del ev, outs, plans, infer, tables
+    torch.cuda.empty_cache()
+    # config 4 (fit half): 200-node card-4 partial 8-tree, counting throughput on a resident chunk
+    spec = synth.random_ktree_dag()
+    tables = tables_from_spec(spec, dev)
+    n_chunk = args.fit_chunk
+    codes = sample_network(spec, seed=1237, first=rank * n_chunk, n=n_chunk, device=dev, tables=tables)
+    torch.cuda.synchronize()
+
+    def cstep(_i):
+        tables.counts.zero_()
+        tables.n_total = 0
+        sharding.fit_sharded(tables, codes, n_chunk)
+
+    k = max(3, min(args.steps, 5))
+    sec = timed(cstep, k, 2)
+    rate = n_chunk * world * k / sec
+    out["ktree200_fit"] = {"metric": "CPT-fit samples/sec", "value": rate, "unit": "samples/s", "n_vars": spec.n,
+                           "samples_per_gpu_per_step": n_chunk, "family_groups": tables.count_groups(),
+                           "achieved_GBs": rate * spec.n / 1e9, "frac_of_hbm_peak": rate * spec.n / 1e9 / (peak_gbs * world)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--fit-chunk", type=int, default=1 << 24)
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

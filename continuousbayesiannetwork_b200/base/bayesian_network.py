@@ -1,0 +1,199 @@
+"""Network API -- same constructor and methods as the reference's ``BayesianNetwork``
+(cbn/base/bayesian_network.py:17-373), running on the B200 engine.
+
+Differences a reference user will notice (all on paths where the reference is broken
+or undefined):
+
+* ``infer`` answers with true Variable Elimination for any DAG / evidence set, not the
+  mean-and-product heuristic.  On the only shape where the reference is a posterior
+  (star DAG, every parent of the target observed) the results agree: identical with
+  ``normalization="global_max"`` (the reference divides the batch by one global max,
+  :296), equal up to that scale with the default ``"row"`` (rows sum to 1).
+* all nodes are fitted by ONE fused pass over an integer-coded sample matrix instead of
+  a Python loop of ``torch.unique`` sorts (:138-160).
+* ``evidence=None`` works (prior marginal); ``do`` performs graph surgery.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import networkx as nx
+import numpy as np
+import torch
+
+from . import BASE_MAX_CARDINALITY, KEY_MAX_CARDINALITY_FOR_DISCRETE
+from .node import Node
+from ..tables import DiscreteTables
+from ..utils import choose_inference_obj
+
+
+class BayesianNetwork:
+    def __init__(self, dag: nx.DiGraph, data, parameters_learning_config: Dict, inference_config: Dict, **kwargs):
+        if not nx.is_directed_acyclic_graph(dag):
+            raise ValueError("The provided graph is not a directed acyclic graph (DAG).")
+
+        self.initial_dag = dag
+        self.column_mapping = {node: i for i, node in enumerate(self.initial_dag.nodes)}
+        self.device = kwargs.get("device", "cuda")
+        kwargs["device"] = self.device
+        self.min_tolerance = kwargs.get("min_tolerance", 1e-10)
+        self.uncertainty = kwargs.get("uncertainty", 1e-10)
+        self.max_cardinality_for_discrete_domain = kwargs.get(KEY_MAX_CARDINALITY_FOR_DISCRETE, BASE_MAX_CARDINALITY)
+        self.log = kwargs.get("log", False)
+        self.nodes_obj = None
+        self.tables: DiscreteTables = None
+        self.inference_obj = None
+        self._kwargs = kwargs
+
+        self._setup_inference(inference_config)
+        self._setup_parameters_learning(data, parameters_learning_config, **kwargs)
+
+    # ------------------------------------------------------------------ setup
+    def _setup_parameters_learning(self, data, config: Dict, **kwargs):
+        estimator_name = config["estimator_name"]
+        self.nodes_obj = {
+            node: Node(node, estimator_name, config, self.get_parents(self.initial_dag, node), **kwargs)
+            for node in self.initial_dag.nodes
+        }
+        self._train(data, self.initial_dag.nodes)
+
+    def _setup_inference(self, config: Dict):
+        self.inference_obj_name = config["inference_obj"]
+        self.inference_obj = choose_inference_obj(self.inference_obj_name, config, device=self.device)
+
+    def save_model(self, path: str):
+        """One file with every count table and domain (the reference's version calls a method that
+        does not exist, bayesian_network.py:78-80)."""
+        t = self.tables
+        torch.save({"names": t.names, "parents": t.parents, "domains": [d.cpu() for d in t.domains],
+                    "counts": t.counts.cpu(), "n_total": t.n_total}, path)
+
+    def load_model(self, path: str):
+        sd = torch.load(path)
+        if list(sd["names"]) != list(self.tables.names):
+            raise ValueError("saved model has different nodes")
+        self.tables.set_domains(sd["domains"])
+        self.tables.counts.copy_(sd["counts"].to(self.tables.device))
+        self.tables.n_total = int(sd["n_total"])
+        self.tables.finalize()
+        self._attach_all()
+
+    # ------------------------------------------------------------------ graph helpers
+    @staticmethod
+    def get_nodes(dag: nx.DiGraph):
+        return sorted(list(dag.nodes))
+
+    def _node_name(self, node):
+        if isinstance(node, str):
+            return node
+        if isinstance(node, int):
+            return next((k for k, v in self.column_mapping.items() if v == node), None)
+        raise ValueError(f"{node} type not supported.")
+
+    def get_ancestors(self, dag: nx.DiGraph, node):
+        name = self._node_name(node)
+        if name is None:
+            return set()
+        ancestors = nx.ancestors(dag, name)
+        ordered = list(nx.topological_sort(dag.subgraph(ancestors | {name})))
+        ordered.remove(name)
+        return ordered
+
+    def get_parents(self, dag: nx.DiGraph, node):
+        return sorted(list(dag.predecessors(self._node_name(node))))
+
+    def get_children(self, dag: nx.DiGraph, node):
+        return sorted(list(dag.successors(self._node_name(node))))
+
+    @staticmethod
+    def get_structure(dag: nx.DiGraph):
+        return {node: list(dag.predecessors(node)) for node in nx.topological_sort(dag)}
+
+    # ------------------------------------------------------------------ fit
+    def _columns(self, data) -> Dict[str, torch.Tensor]:
+        """float32 device column per node.  DataFrames go through ONE numpy block and one H2D copy
+        (the reference does pandas -> list -> numpy -> torch per column, :144-157); dicts of tensors /
+        arrays are taken as they are (GPU-resident data is not copied)."""
+        names = list(self.initial_dag.nodes)
+        dev = self.device
+        if isinstance(data, dict):
+            return {n: torch.as_tensor(data[n]).reshape(-1).to(dev, torch.float32) for n in names}
+        missing = [n for n in names if n not in data.columns]
+        if missing:
+            raise ValueError(f"data has no column for nodes {missing}")
+        block = np.ascontiguousarray(data[names].to_numpy(dtype=np.float32).T)      # [n_vars, n]
+        dev_block = torch.from_numpy(block).to(dev)
+        return {n: dev_block[i] for i, n in enumerate(names)}
+
+    def _train(self, data, pbar: Iterable = None):
+        names = list(self.initial_dag.nodes)
+        parents = {n: self.get_parents(self.initial_dag, n) for n in names}
+        cols = self._columns(data)
+        self.tables = DiscreteTables(names, parents, device=self.device)
+        self.tables.fit_columns(cols)
+        self._attach_all()
+
+    def _attach_all(self):
+        for n, node in self.nodes_obj.items():
+            node.attach(self.tables, n)
+        self.inference_obj.bind(self.tables)
+
+    def update_knowledge(self, data, accumulate: bool = False):
+        """Re-fit on ``data`` (the reference REPLACES the tables: brute_force.py:47).  With
+        ``accumulate=True`` the new samples are added to the existing int64 count tables instead
+        (values outside the fitted domains raise ValueError)."""
+        if not accumulate:
+            self._train(data)
+            return
+        cols = self._columns(data)
+        codes = self.tables.encode_columns(cols, strict=True)
+        self.tables.count(codes, int(next(iter(cols.values())).numel()))
+        self.tables.finalize()
+        self._attach_all()
+
+    # ------------------------------------------------------------------ queries
+    def get_pdf(self, target_node: str, evidence: Dict, N_max: int = 1024) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Factor of one node: only the evidence on its parents is used (reference :176-206)."""
+        target_node_parents = self.get_parents(self.initial_dag, target_node)
+        query = {f: v for f, v in (evidence or {}).items() if f in target_node_parents}
+        return self.nodes_obj[target_node].get_prob(query, N_max)
+
+    def infer(self, target_node: str, evidence: Dict[str, torch.Tensor] = None, do: List[str] = None,
+              N_max: int = 16, plot_prob=False, normalization: str = None):
+        """
+        :param target_node: node whose posterior is computed
+        :param evidence: name -> tensor [n_queries, 1] of observed VALUES
+        :param do: names of evidence variables that are interventions
+        :param N_max: number of evaluation points of the target domain (reference semantics, node.py:286-300):
+                      ``N_max >= card(target)`` evaluates the whole domain, smaller values sub-sample it
+        :return: (pdf [n_queries, V], domains [n_queries, V])
+        """
+        if target_node not in self.nodes_obj:
+            raise ValueError(f"{target_node} is not a node of the network")
+        kw = {} if normalization is None else {"normalization": normalization}
+        pdf = self.inference_obj.infer(target_node, evidence or {}, do, **kw)
+        dom = self.tables.domains[self.tables.index[target_node]]
+        if N_max < dom.shape[0]:
+            idx = torch.linspace(0, dom.shape[0] - 1, N_max).round().long().to(dom.device)
+            pdf = pdf[:, idx].contiguous()
+            dom = dom[idx]
+        domains = dom.unsqueeze(0).expand(pdf.shape[0], -1)
+        assert pdf.shape == domains.shape, "pdf and domain must have same shape."
+        return pdf, domains
+
+    def infer_map(self, target_node: str, evidence: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """MAP value of the target per row (what ``benchmarking_df`` extracts, :357-366)."""
+        pdf, dom = self.infer(target_node, evidence, N_max=1 << 30)
+        return torch.gather(dom, 1, torch.argmax(pdf, dim=1, keepdim=True)).squeeze(1)
+
+    def benchmarking_df(self, data, target_feature: str, batch_size: int = 128, **kwargs) -> np.ndarray:
+        """Batched MAP prediction with every other column as evidence (reference :329-373).  The whole
+        frame is one launch per ``batch_size`` rows; pass a large batch_size to do it in one."""
+        feats = [f for f in data.columns if f != target_feature and f in self.nodes_obj]
+        block = torch.from_numpy(np.ascontiguousarray(data[feats].to_numpy(dtype=np.float32).T)).to(self.device)
+        n = block.shape[1]
+        pred = torch.empty(n, dtype=torch.float32, device=self.device)
+        for s in range(0, n, batch_size):
+            ev = {f: block[i, s: s + batch_size].unsqueeze(-1) for i, f in enumerate(feats)}
+            pred[s: s + batch_size] = self.infer_map(target_feature, ev)
+        return pred.cpu().numpy().astype(np.float64)

@@ -1,0 +1,102 @@
+// Shared host/device helpers for the cbn_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "cbn_b200.h"
+
+struct cbn_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  std::string err;
+  // internal streams / staging for the host-buffer entry points
+  cudaStream_t io_stream[2] = {nullptr, nullptr};
+  cudaEvent_t io_event[2] = {nullptr, nullptr};
+  void* io_dev_in[2] = {nullptr, nullptr};
+  void* io_dev_out[2] = {nullptr, nullptr};
+  void* io_pin_in[2] = {nullptr, nullptr};
+  void* io_pin_out[2] = {nullptr, nullptr};
+  size_t io_in_bytes = 0, io_out_bytes = 0;
+};
+
+extern thread_local std::string cbn_tls_error;
+
+inline int cbn_fail(cbn_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  cbn_tls_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CBN_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return cbn_fail((ctx), CBN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define CBN_CHECK_LAUNCH(ctx) CBN_CUDA(ctx, cudaGetLastError())
+
+// RAII: run on ctx->device without disturbing the caller's (torch's) current device.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      changed = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_nc_u128(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_nc_f128(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_na_f128(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// exact-match search of x in a sorted domain; CBN_UNSEEN if absent (float equality, as the
+// reference keys categories: brute_force.py:228)
+__device__ __forceinline__ int domain_code(const float* __restrict__ dom, int card, float x) {
+  int lo = 0, hi = card;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (dom[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return (lo < card && dom[lo] == x) ? lo : CBN_UNSEEN;
+}

@@ -1,0 +1,838 @@
+// CPT fitting path: domain discovery, encoding, family counting, normalisation, mle rows,
+// conditional lookup.  Replaces BruteForce._fit / _get_prob
+// (reference cbn/parameter_learning/brute_force.py:17-53, :172-244) and the domain
+// bookkeeping of Node.fit (cbn/base/node.py:85-110).
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+thread_local std::string cbn_tls_error;
+
+// =========================================================================== context
+extern "C" int cbn_abi_version(void) { return CBN_ABI_VERSION; }
+
+extern "C" int cbn_ctx_create(int device, cbn_ctx** out) {
+  if (!out) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ctx_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return cbn_fail(nullptr, CBN_ERR_CUDA, "cbn_ctx_create: no CUDA device (%s)", cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ctx_create: device %d out of range [0,%d)", device, count);
+  cbn_ctx* ctx = new (std::nothrow) cbn_ctx();
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_NOMEM, "cbn_ctx_create: out of host memory");
+  ctx->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return cbn_fail(nullptr, CBN_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    delete ctx;
+    return cbn_fail(nullptr, CBN_ERR_UNSUPPORTED,
+                    "cbn_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = ctx;
+  return CBN_OK;
+}
+
+extern "C" void cbn_ctx_destroy(cbn_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->io_stream[i]) cudaStreamDestroy(ctx->io_stream[i]);
+    if (ctx->io_event[i]) cudaEventDestroy(ctx->io_event[i]);
+    if (ctx->io_dev_in[i]) cudaFree(ctx->io_dev_in[i]);
+    if (ctx->io_dev_out[i]) cudaFree(ctx->io_dev_out[i]);
+    if (ctx->io_pin_in[i]) cudaFreeHost(ctx->io_pin_in[i]);
+    if (ctx->io_pin_out[i]) cudaFreeHost(ctx->io_pin_out[i]);
+  }
+  delete ctx;
+}
+
+extern "C" const char* cbn_last_error(cbn_ctx* ctx) { return ctx ? ctx->err.c_str() : cbn_tls_error.c_str(); }
+extern "C" int cbn_device_sm_count(cbn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+static int check_family(cbn_ctx* ctx, const cbn_family* f, int n_cols, int64_t* n_cells_out) {
+  if (f->n_vars < 1 || f->n_vars > CBN_MAX_FAMILY_VARS)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "family has %d variables (supported: 1..%d)", f->n_vars,
+                    CBN_MAX_FAMILY_VARS);
+  int64_t cells = 1;
+  for (int j = 0; j < f->n_vars; ++j) {
+    if (n_cols >= 0 && (f->var[j] < 0 || f->var[j] >= n_cols))
+      return cbn_fail(ctx, CBN_ERR_INVALID, "family variable %d is not a column in [0,%d)", f->var[j], n_cols);
+    if (f->card[j] < 1 || f->card[j] > CBN_MAX_CARD)
+      return cbn_fail(ctx, CBN_ERR_INVALID, "cardinality %d outside [1,%d]", f->card[j], CBN_MAX_CARD);
+    cells *= f->card[j];
+    if (cells > (int64_t(1) << 31))
+      return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "family table larger than 2^31 cells");
+  }
+  *n_cells_out = cells;
+  return CBN_OK;
+}
+
+// =========================================================================== domain discovery
+// Distinct values of a float column (<= 255 of them) with a two-level hash set: a
+// shared-memory set per CTA, merged into a global set, then sorted by one CTA.
+namespace {
+constexpr int DOM_SLOTS = 1024;            // power of two, > 2 * CBN_MAX_CARD
+constexpr uint32_t DOM_EMPTY = 0x7fc00001u;  // a NaN payload no canonicalised input can equal
+
+__device__ __forceinline__ uint32_t canon_bits(float x) {
+  if (x == 0.0f) x = 0.0f;                       // -0 -> +0
+  uint32_t b = __float_as_uint(x);
+  if (x != x) b = 0x7fc00000u;                   // all NaNs collapse (the reference would keep each)
+  return b;
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// returns false when the set is full
+__device__ __forceinline__ bool set_insert(uint32_t* set, uint32_t bits) {
+  uint32_t h = hash32(bits) & (DOM_SLOTS - 1);
+  for (int probe = 0; probe < DOM_SLOTS; ++probe) {
+    uint32_t cur = set[h];
+    if (cur == bits) return true;
+    if (cur == DOM_EMPTY) {
+      uint32_t old = atomicCAS(&set[h], DOM_EMPTY, bits);
+      if (old == DOM_EMPTY || old == bits) return true;
+    } else {
+      h = (h + 1) & (DOM_SLOTS - 1);
+      continue;
+    }
+    // lost the race to a different value: re-read the same slot
+    if (set[h] != bits) h = (h + 1) & (DOM_SLOTS - 1);
+  }
+  return false;
+}
+
+__global__ void domain_init_kernel(uint32_t* gset, int* overflow) {
+  for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) gset[i] = DOM_EMPTY;
+  if (threadIdx.x == 0) *overflow = 0;
+}
+
+__global__ void __launch_bounds__(256) domain_scan_kernel(const float* __restrict__ col, int64_t n,
+                                                          uint32_t* gset, int* overflow) {
+  __shared__ uint32_t sset[DOM_SLOTS];
+  for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) sset[i] = DOM_EMPTY;
+  __syncthreads();
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  uint32_t last = DOM_EMPTY;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t b = canon_bits(__ldg(col + i));
+    if (b == last) continue;  // runs of equal values are the common case
+    last = b;
+    // fast path: already present
+    uint32_t h = hash32(b) & (DOM_SLOTS - 1);
+    if (sset[h] == b) continue;
+    if (!set_insert(sset, b)) {
+      atomicExch(overflow, 1);   // more than DOM_SLOTS distinct values: not a discrete column, stop early
+      break;
+    }
+    if (*reinterpret_cast<volatile int*>(overflow)) break;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) {
+    uint32_t b = sset[i];
+    if (b != DOM_EMPTY) {
+      if (!set_insert(gset, b)) atomicExch(overflow, 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DOM_SLOTS) domain_finish_kernel(const uint32_t* gset, const int* overflow,
+                                                                  float* domain_out, int32_t* card_out) {
+  __shared__ float vals[DOM_SLOTS];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  uint32_t b = gset[threadIdx.x];
+  if (b != DOM_EMPTY) atomicAdd(&s_n, 1);
+  // +inf padding sorts last; NaN (0x7fc00000) is mapped to +inf-like ordering by bit trick below
+  vals[threadIdx.x] = (b != DOM_EMPTY) ? __uint_as_float(b) : __int_as_float(0x7f800000);
+  __syncthreads();
+  // bitonic sort of DOM_SLOTS floats (NaN treated as larger than everything)
+  for (int k = 2; k <= DOM_SLOTS; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      int ixj = threadIdx.x ^ j;
+      if (ixj > threadIdx.x) {
+        float a = vals[threadIdx.x], c = vals[ixj];
+        bool up = (threadIdx.x & k) == 0;
+        bool gt = (a > c) || (a != a && c == c);
+        if (gt == up) { vals[threadIdx.x] = c; vals[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  int n = s_n;
+  if (*overflow || n > CBN_MAX_CARD) {
+    if (threadIdx.x == 0) *card_out = -1;
+    return;
+  }
+  if (threadIdx.x < 256) domain_out[threadIdx.x] = threadIdx.x < n ? vals[threadIdx.x] : 0.0f;
+  if (threadIdx.x == 0) *card_out = n;
+}
+}  // namespace
+
+extern "C" int cbn_domain_f32(cbn_ctx* ctx, const float* col, int64_t n, float* domain_out, int32_t* card_out,
+                              cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_domain_f32: ctx is NULL");
+  if (!col || !domain_out || !card_out || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_domain_f32: bad argument");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* gset = nullptr;
+  CBN_CUDA(ctx, cudaMallocAsync((void**)&gset, (DOM_SLOTS + 1) * sizeof(uint32_t), s));
+  int* overflow = reinterpret_cast<int*>(gset + DOM_SLOTS);
+  domain_init_kernel<<<1, 256, 0, s>>>(gset, overflow);
+  if (n > 0) {
+    int blocks = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), int64_t(ctx->sm_count) * 8);
+    domain_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
+  }
+  domain_finish_kernel<<<1, DOM_SLOTS, 0, s>>>(gset, overflow, domain_out, card_out);
+  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, cudaFreeAsync(gset, s));
+  return CBN_OK;
+}
+
+// =========================================================================== encode
+namespace {
+template <bool VEC>
+__global__ void __launch_bounds__(256) encode_f32_kernel(const float* __restrict__ col, int64_t n,
+                                                         const float* __restrict__ dom, int card,
+                                                         uint8_t* __restrict__ codes,
+                                                         unsigned long long* n_unseen) {
+  __shared__ float sdom[256];
+  for (int i = threadIdx.x; i < card; i += blockDim.x) sdom[i] = dom[i];
+  __syncthreads();
+  unsigned int unseen = 0;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 v = ld_nc_f128(reinterpret_cast<const float4*>(col) + i);
+      int c0 = domain_code(sdom, card, v.x), c1 = domain_code(sdom, card, v.y);
+      int c2 = domain_code(sdom, card, v.z), c3 = domain_code(sdom, card, v.w);
+      unseen += (c0 == CBN_UNSEEN) + (c1 == CBN_UNSEEN) + (c2 == CBN_UNSEEN) + (c3 == CBN_UNSEEN);
+      reinterpret_cast<uint32_t*>(codes)[i] = uint32_t(c0) | (uint32_t(c1) << 8) | (uint32_t(c2) << 16) | (uint32_t(c3) << 24);
+    }
+    // tail
+    for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      int c = domain_code(sdom, card, col[i]);
+      unseen += (c == CBN_UNSEEN);
+      codes[i] = (uint8_t)c;
+    }
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      int c = domain_code(sdom, card, col[i]);
+      unseen += (c == CBN_UNSEEN);
+      codes[i] = (uint8_t)c;
+    }
+  }
+  if (n_unseen) {
+    for (int o = 16; o > 0; o >>= 1) unseen += __shfl_xor_sync(0xffffffffu, unseen, o);
+    if ((threadIdx.x & 31) == 0 && unseen) atomicAdd(n_unseen, (unsigned long long)unseen);
+  }
+}
+}  // namespace
+
+extern "C" int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const float* sorted_domain, int32_t card,
+                              uint8_t* codes_out, unsigned long long* n_unseen, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_encode_f32: ctx is NULL");
+  if (!col || !sorted_domain || !codes_out || n < 0 || card < 1 || card > CBN_MAX_CARD)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_encode_f32: bad argument (card=%d, n=%lld)", card, (long long)n);
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = is_aligned(col, 16) && is_aligned(codes_out, 4);
+  int64_t work = vec ? (n + 3) / 4 : n;
+  int blocks = (int)std::min<int64_t>((work + 255) / 256, int64_t(ctx->sm_count) * 16);
+  if (vec) encode_f32_kernel<true><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
+  else encode_f32_kernel<false><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+// =========================================================================== counting
+namespace {
+struct FamRec {          // 112 bytes, one per family, ordered by group
+  int32_t n_vars;
+  int32_t smem_off;      // first cell inside the group's shared-memory table
+  int32_t n_cells;
+  int32_t reserved;
+  int32_t var[CBN_MAX_FAMILY_VARS];
+  int32_t stride[CBN_MAX_FAMILY_VARS];
+};
+constexpr int COUNT_TPB = 256;
+constexpr int COUNT_MAX_GROUP_FAMS = 256;
+}  // namespace
+
+struct cbn_count_plan {
+  int device = 0;
+  int n_fams = 0, n_cols = 0, n_groups = 0, n_large = 0;
+  int max_group_cells = 0, max_group_fams = 0;
+  std::vector<int> group_start;   // [n_groups+1] into recs
+  FamRec* d_recs = nullptr;       // small families first (grouped), then large ones
+  int* d_group_start = nullptr;
+  long long* d_goff = nullptr;    // global table offset per rec
+  int sm_count = 148;
+  size_t smem_cap_cells = 0;
+};
+
+namespace {
+// One CTA = one family group x a strided set of sample quads.  Tables of the group live in
+// shared memory as uint32 counters; every thread owns 4 consecutive samples per step (one
+// 32-bit load per column, coalesced 128 B per warp).
+__global__ void __launch_bounds__(COUNT_TPB) count_families_kernel(
+    const uint8_t* __restrict__ codes, int64_t ld, int64_t n, const FamRec* __restrict__ recs,
+    const int* __restrict__ group_start, const long long* __restrict__ goff,
+    unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int g = blockIdx.y;
+  const int f0 = group_start[g], f1 = group_start[g + 1];
+  const int nf = f1 - f0;
+  FamRec* srec = reinterpret_cast<FamRec*>(smem_u32);
+  uint32_t* tbl = smem_u32 + (size_t(nf) * sizeof(FamRec)) / 4;
+  for (int i = threadIdx.x; i < nf * int(sizeof(FamRec) / 4); i += blockDim.x)
+    smem_u32[i] = reinterpret_cast<const uint32_t*>(recs + f0)[i];
+  __syncthreads();
+  const int cells = srec[nf - 1].smem_off + srec[nf - 1].n_cells;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) tbl[i] = 0u;
+  __syncthreads();
+
+  const int64_t nquads = n >> 2;
+  const int64_t qstride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += qstride) {
+    for (int f = 0; f < nf; ++f) {
+      const FamRec& r = srec[f];
+      uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+      uint32_t ff = 0;  // != 0 iff some loaded code is CBN_UNSEEN (0xFF): classic "has zero byte" on ~w
+      const int nv = r.n_vars;
+#pragma unroll 4
+      for (int j = 0; j < nv; ++j) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(codes + int64_t(r.var[j]) * ld) + q);
+        const uint32_t st = (uint32_t)r.stride[j];
+        ff |= (~w - 0x01010101u) & w & 0x80808080u;
+        i0 += (w & 0xffu) * st;
+        i1 += ((w >> 8) & 0xffu) * st;
+        i2 += ((w >> 16) & 0xffu) * st;
+        i3 += (w >> 24) * st;
+      }
+      const uint32_t nc = (uint32_t)r.n_cells;
+      uint32_t* t = tbl + r.smem_off;
+      if (ff != 0) {
+        // rare: redo the rows exactly, skipping those that hold an unseen code
+        uint32_t badrow = 0;
+        for (int j = 0; j < nv; ++j) {
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(codes + int64_t(r.var[j]) * ld) + q);
+          badrow |= ((w & 0xffu) == 0xffu ? 1u : 0u) | (((w >> 8) & 0xffu) == 0xffu ? 2u : 0u) |
+                    (((w >> 16) & 0xffu) == 0xffu ? 4u : 0u) | ((w >> 24) == 0xffu ? 8u : 0u);
+        }
+        if (badrow & 1u) i0 = nc;
+        if (badrow & 2u) i1 = nc;
+        if (badrow & 4u) i2 = nc;
+        if (badrow & 8u) i3 = nc;
+      }
+      if (i0 < nc) atomicAdd(t + i0, 1u);
+      if (i1 < nc) atomicAdd(t + i1, 1u);
+      if (i2 < nc) atomicAdd(t + i2, 1u);
+      if (i3 < nc) atomicAdd(t + i3, 1u);
+    }
+  }
+  // tail samples (n % 4) : first CTA of each group, scalar
+  if (blockIdx.x == 0) {
+    for (int64_t s = (nquads << 2) + threadIdx.x; s < n; s += blockDim.x) {
+      for (int f = 0; f < nf; ++f) {
+        const FamRec& r = srec[f];
+        uint32_t idx = 0;
+        bool ok = true;
+        for (int j = 0; j < r.n_vars; ++j) {
+          const uint32_t c = codes[int64_t(r.var[j]) * ld + s];
+          ok &= (c != CBN_UNSEEN);
+          idx += c * (uint32_t)r.stride[j];
+        }
+        if (ok && idx < (uint32_t)r.n_cells) atomicAdd(tbl + r.smem_off + idx, 1u);
+      }
+    }
+  }
+  __syncthreads();
+  // flush the private tables into the caller's int64 tables
+  for (int f = 0; f < nf; ++f) {
+    const FamRec& r = srec[f];
+    unsigned long long* dst = counts + goff[f0 + f];
+    const uint32_t* t = tbl + r.smem_off;
+    for (int c = threadIdx.x; c < r.n_cells; c += blockDim.x) {
+      uint32_t v = t[c];
+      if (v) atomicAdd(dst + c, (unsigned long long)v);
+    }
+  }
+}
+
+// Families whose table does not fit in shared memory: global 64-bit atomics.
+__global__ void __launch_bounds__(COUNT_TPB) count_large_kernel(
+    const uint8_t* __restrict__ codes, int64_t ld, int64_t n, const FamRec* __restrict__ recs, int n_large,
+    const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride) {
+    for (int f = 0; f < n_large; ++f) {
+      const FamRec& r = recs[f];
+      uint32_t idx = 0;
+      bool ok = true;
+      for (int j = 0; j < r.n_vars; ++j) {
+        uint32_t c = codes[int64_t(r.var[j]) * ld + s];
+        ok &= (c != CBN_UNSEEN);
+        idx += c * (uint32_t)r.stride[j];
+      }
+      if (ok && idx < (uint32_t)r.n_cells) atomicAdd(counts + goff[f] + idx, 1ull);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t n_fams, int32_t n_cols,
+                                     cbn_count_plan** out) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_plan_create: ctx is NULL");
+  if (!fams || n_fams < 1 || n_cols < 1 || !out)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_plan_create: bad argument");
+  DeviceGuard g(ctx->device);
+  // shared-memory budget per CTA: two CTAs per SM, leave room for L1
+  const size_t smem_budget = std::min<size_t>(ctx->smem_optin, 96 * 1024);
+  std::vector<FamRec> small, large;
+  std::vector<long long> goff_small, goff_large;
+  std::vector<int> group_start{0};
+  size_t cur_bytes = 0;
+  int cur_fams = 0;
+  int max_cells = 0, max_fams = 0, cur_cells = 0;
+  for (int f = 0; f < n_fams; ++f) {
+    int64_t cells = 0;
+    int rc = check_family(ctx, &fams[f], n_cols, &cells);
+    if (rc) return rc;
+    FamRec r{};
+    r.n_vars = fams[f].n_vars;
+    r.n_cells = (int32_t)cells;
+    int64_t st = 1;
+    for (int j = r.n_vars - 1; j >= 0; --j) {
+      r.var[j] = fams[f].var[j];
+      r.stride[j] = (int32_t)st;
+      st *= fams[f].card[j];
+    }
+    size_t need = size_t(cells) * 4 + sizeof(FamRec);
+    if (need + 64 > smem_budget) {
+      large.push_back(r);
+      goff_large.push_back(fams[f].table_offset);
+      continue;
+    }
+    if (cur_bytes + need > smem_budget || cur_fams >= COUNT_MAX_GROUP_FAMS) {
+      group_start.push_back((int)small.size());
+      max_cells = std::max(max_cells, cur_cells);
+      max_fams = std::max(max_fams, cur_fams);
+      cur_bytes = 0; cur_fams = 0; cur_cells = 0;
+    }
+    r.smem_off = cur_cells;
+    small.push_back(r);
+    goff_small.push_back(fams[f].table_offset);
+    cur_bytes += need; cur_fams += 1; cur_cells += (int)cells;
+  }
+  if (cur_fams > 0) {
+    group_start.push_back((int)small.size());
+    max_cells = std::max(max_cells, cur_cells);
+    max_fams = std::max(max_fams, cur_fams);
+  }
+  cbn_count_plan* p = new (std::nothrow) cbn_count_plan();
+  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
+  p->device = ctx->device;
+  p->n_fams = n_fams; p->n_cols = n_cols;
+  p->n_groups = (int)group_start.size() - 1;
+  p->n_large = (int)large.size();
+  p->max_group_cells = max_cells; p->max_group_fams = max_fams;
+  p->group_start = group_start;
+  p->sm_count = ctx->sm_count;
+  std::vector<FamRec> all = small;
+  all.insert(all.end(), large.begin(), large.end());
+  std::vector<long long> goff = goff_small;
+  goff.insert(goff.end(), goff_large.begin(), goff_large.end());
+  cudaError_t e;
+  if ((e = cudaMalloc((void**)&p->d_recs, all.size() * sizeof(FamRec))) != cudaSuccess ||
+      (e = cudaMalloc((void**)&p->d_group_start, group_start.size() * sizeof(int))) != cudaSuccess ||
+      (e = cudaMalloc((void**)&p->d_goff, goff.size() * sizeof(long long))) != cudaSuccess) {
+    cbn_count_plan_destroy(p);
+    return cbn_fail(ctx, CBN_ERR_CUDA, "cudaMalloc (count plan): %s", cudaGetErrorString(e));
+  }
+  cudaMemcpy(p->d_recs, all.data(), all.size() * sizeof(FamRec), cudaMemcpyHostToDevice);
+  cudaMemcpy(p->d_group_start, group_start.data(), group_start.size() * sizeof(int), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(p->d_goff, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cbn_count_plan_destroy(p);
+    return cbn_fail(ctx, CBN_ERR_CUDA, "cudaMemcpy (count plan): %s", cudaGetErrorString(e));
+  }
+  if (p->n_groups > 0) {
+    size_t smem = size_t(max_fams) * sizeof(FamRec) + size_t(max_cells) * 4;
+    // the kernel indexes with the group's own family count, but the allocation is the max
+    smem = 0;
+    for (int gi = 0; gi < p->n_groups; ++gi) {
+      int a = group_start[gi], b = group_start[gi + 1];
+      size_t s = size_t(b - a) * sizeof(FamRec) + size_t(small[b - 1].smem_off + small[b - 1].n_cells) * 4;
+      smem = std::max(smem, s);
+    }
+    p->smem_cap_cells = smem;
+    e = cudaFuncSetAttribute(count_families_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cbn_count_plan_destroy(p);
+      return cbn_fail(ctx, CBN_ERR_CUDA, "cudaFuncSetAttribute(count): %s", cudaGetErrorString(e));
+    }
+  }
+  *out = p;
+  return CBN_OK;
+}
+
+extern "C" void cbn_count_plan_destroy(cbn_count_plan* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  if (p->d_recs) cudaFree(p->d_recs);
+  if (p->d_group_start) cudaFree(p->d_group_start);
+  if (p->d_goff) cudaFree(p->d_goff);
+  delete p;
+}
+
+extern "C" int cbn_count_plan_groups(const cbn_count_plan* plan) { return plan ? plan->n_groups + (plan->n_large > 0) : 0; }
+
+extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
+                             unsigned long long* counts, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run: ctx is NULL");
+  if (!plan || !codes || !counts || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
+  if (ld < n || (ld % 16) != 0 || !is_aligned(codes, 16))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: code matrix needs ld >= n, ld %% 16 == 0 and a 16-byte aligned base (ld=%lld, n=%lld)",
+                    (long long)ld, (long long)n);
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t chunk = int64_t(1) << 33;  // uint32 private counters cannot overflow below this
+  for (int64_t start = 0; start < n; start += chunk) {
+    const int64_t m = std::min(chunk, n - start);  // start is a multiple of 2^33, alignment is preserved
+    const uint8_t* base = codes + start;
+    if (plan->n_groups > 0) {
+      int64_t quads = std::max<int64_t>(m >> 2, 1);
+      int64_t want = (quads + COUNT_TPB - 1) / COUNT_TPB;
+      int per_group = std::max(1, (2 * plan->sm_count + plan->n_groups - 1) / plan->n_groups);
+      // a few waves per group so the flush cost stays small next to the pass itself
+      int gx = (int)std::min<int64_t>(want, per_group);
+      dim3 grid(gx, plan->n_groups);
+      count_families_kernel<<<grid, COUNT_TPB, plan->smem_cap_cells, s>>>(base, ld, m, plan->d_recs, plan->d_group_start,
+                                                                          plan->d_goff, counts);
+      CBN_CHECK_LAUNCH(ctx);
+    }
+    if (plan->n_large > 0) {
+      int small_n = plan->group_start.empty() ? 0 : plan->group_start.back();
+      int blocks = (int)std::min<int64_t>((m + COUNT_TPB - 1) / COUNT_TPB, int64_t(plan->sm_count) * 8);
+      count_large_kernel<<<blocks, COUNT_TPB, 0, s>>>(base, ld, m, plan->d_recs + small_n, plan->n_large,
+                                                      plan->d_goff + small_n, counts);
+      CBN_CHECK_LAUNCH(ctx);
+    }
+  }
+  return CBN_OK;
+}
+
+// =========================================================================== counts -> probabilities
+namespace {
+struct CptFam {
+  long long off;
+  int n_rows;   // parent configurations
+  int card;     // node cardinality
+};
+
+__global__ void __launch_bounds__(256) cpt_from_counts_kernel(const long long* __restrict__ counts,
+                                                              const CptFam* __restrict__ fams, float n_total,
+                                                              float* __restrict__ joint, float* __restrict__ cond) {
+  const CptFam f = fams[blockIdx.y];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < f.n_rows; r += gridDim.x * blockDim.x) {
+    const long long base = f.off + (long long)r * f.card;
+    float parent = 0.0f;
+    for (int x = 0; x < f.card; ++x) {
+      float j = __fdiv_rn(__ll2float_rn(counts[base + x]), n_total);
+      if (joint) joint[base + x] = j;
+      parent = __fadd_rn(parent, j);
+    }
+    if (cond) {
+      const float den = __fadd_rn(parent, 1e-10f);
+      for (int x = 0; x < f.card; ++x) {
+        float j = __fdiv_rn(__ll2float_rn(counts[base + x]), n_total);
+        cond[base + x] = __fdiv_rn(j, den);
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const cbn_family* fams, int32_t n_fams,
+                                   long long n_total, float* joint, float* cond, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_cpt_from_counts: ctx is NULL");
+  if (!counts || !fams || n_fams < 1 || n_total < 1 || (!joint && !cond))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_cpt_from_counts: bad argument");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<CptFam> h(n_fams);
+  int max_rows = 1;
+  for (int f = 0; f < n_fams; ++f) {
+    int64_t cells = 0;
+    int rc = check_family(ctx, &fams[f], -1, &cells);
+    if (rc) return rc;
+    h[f].off = fams[f].table_offset;
+    h[f].card = fams[f].card[fams[f].n_vars - 1];
+    h[f].n_rows = (int)(cells / h[f].card);
+    max_rows = std::max(max_rows, h[f].n_rows);
+  }
+  CptFam* d = nullptr;
+  CBN_CUDA(ctx, cudaMallocAsync((void**)&d, sizeof(CptFam) * n_fams, s));
+  CBN_CUDA(ctx, cudaMemcpyAsync(d, h.data(), sizeof(CptFam) * n_fams, cudaMemcpyHostToDevice, s));
+  // pageable source: the copy above is staged before the call returns, h may go out of scope
+  for (int f0 = 0; f0 < n_fams; f0 += 65535) {
+    int nf = std::min(65535, n_fams - f0);
+    dim3 grid(std::min((max_rows + 255) / 256, 1024), nf);
+    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d + f0, (float)n_total, joint, cond);
+  }
+  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, cudaFreeAsync(d, s));
+  return CBN_OK;
+}
+
+// =========================================================================== mle_tensor rows
+namespace {
+struct MleParams {
+  int n_vars;
+  int card[CBN_MAX_FAMILY_VARS];
+  const float* dom[CBN_MAX_FAMILY_VARS];
+  long long n_cells;
+};
+
+__global__ void __launch_bounds__(1024) mle_from_counts_kernel(const long long* __restrict__ counts, MleParams p,
+                                                               float n_total, float* __restrict__ mle,
+                                                               long long* __restrict__ n_rows_out) {
+  __shared__ int warp_tot[32];
+  __shared__ long long s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int width = p.n_vars + 1;
+  for (long long c0 = 0; c0 < p.n_cells; c0 += blockDim.x) {
+    long long c = c0 + threadIdx.x;
+    long long cnt = (c < p.n_cells) ? counts[c] : 0;
+    bool keep = cnt > 0;
+    unsigned b = __ballot_sync(0xffffffffu, keep);
+    int within = __popc(b & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[wid] = __popc(b);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      int t = warp_tot[w];
+      if (w < wid) before += t;
+      total += t;
+    }
+    long long base = s_base;
+    if (keep) {
+      long long row = base + before + within;
+      long long rem = c;
+      float* dst = mle + row * width;
+      for (int j = p.n_vars - 1; j >= 0; --j) {
+        int code = (int)(rem % p.card[j]);
+        rem /= p.card[j];
+        dst[j] = p.dom[j][code];
+      }
+      dst[p.n_vars] = __fdiv_rn(__ll2float_rn(cnt), n_total);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_rows_out = s_base;
+}
+}  // namespace
+
+extern "C" int cbn_mle_from_counts(cbn_ctx* ctx, const long long* counts, const cbn_family* fam,
+                                   const float* const* domains, long long n_total, float* mle_out,
+                                   long long* n_rows_out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_mle_from_counts: ctx is NULL");
+  if (!counts || !fam || !domains || !mle_out || !n_rows_out || n_total < 1)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_mle_from_counts: bad argument");
+  int64_t cells = 0;
+  int rc = check_family(ctx, fam, -1, &cells);
+  if (rc) return rc;
+  DeviceGuard g(ctx->device);
+  MleParams p{};
+  p.n_vars = fam->n_vars;
+  p.n_cells = cells;
+  for (int j = 0; j < fam->n_vars; ++j) {
+    p.card[j] = fam->card[j];
+    p.dom[j] = domains[j];
+    if (!domains[j]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_mle_from_counts: domain %d is NULL", j);
+  }
+  mle_from_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, p, (float)n_total, mle_out, n_rows_out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+// =========================================================================== conditional lookup
+namespace {
+struct ProbParams {
+  int n_vars;                             // parents + node
+  int card[CBN_MAX_FAMILY_VARS];
+  int dom_off[CBN_MAX_FAMILY_VARS];       // offsets into the shared-memory domain pool
+  const float* dom[CBN_MAX_FAMILY_VARS];
+  int dom_total;
+  long long n_pa_rows;                    // product of parent cards
+};
+
+__global__ void __launch_bounds__(256) get_prob_kernel(const float* __restrict__ table, ProbParams p,
+                                                       const float* __restrict__ points, long long points_rows,
+                                                       int n_values, const float* __restrict__ query,
+                                                       long long n_queries, float* __restrict__ out) {
+  extern __shared__ float sdom[];
+  for (int j = 0; j < p.n_vars; ++j)
+    for (int i = threadIdx.x; i < p.card[j]; i += blockDim.x) sdom[p.dom_off[j] + i] = p.dom[j][i];
+  __syncthreads();
+  const int P = p.n_vars - 1;
+  const int cx = p.card[P];
+  const float* xdom = sdom + p.dom_off[P];
+  const long long total = n_queries * n_values;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / n_values;
+    const int v = (int)(i - q * n_values);
+    const float x = points[(points_rows == 1 ? 0 : q) * n_values + v];
+    const int xc = domain_code(xdom, cx, x);
+    float r = 0.0f;
+    if (xc != CBN_UNSEEN) {
+      if (query) {
+        long long pa = 0;
+        bool ok = true;
+        for (int j = 0; j < P; ++j) {
+          int c = domain_code(sdom + p.dom_off[j], p.card[j], query[q * P + j]);
+          ok &= (c != CBN_UNSEEN);
+          pa = pa * p.card[j] + c;
+        }
+        if (ok) r = table[pa * cx + xc];
+      } else {
+        // marginal branch (brute_force.py:192-201): sum the joint over the parent rows, in row order
+        for (long long pa = 0; pa < p.n_pa_rows; ++pa) r = __fadd_rn(r, table[pa * cx + xc]);
+      }
+    }
+    out[i] = r;
+  }
+}
+}  // namespace
+
+extern "C" int cbn_get_prob_f32(cbn_ctx* ctx, const float* table, const cbn_family* fam, const float* const* domains,
+                                const float* points, int64_t points_rows, int32_t n_values, const float* query,
+                                int64_t n_queries, float* out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_get_prob_f32: ctx is NULL");
+  if (!table || !fam || !domains || !points || !out || n_values < 1 || n_queries < 0)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_get_prob_f32: bad argument");
+  if (points_rows != 1 && points_rows != n_queries)
+    return cbn_fail(ctx, CBN_ERR_INVALID,
+                    "'point_to_evaluate' first dimension must match number of queries. Got %lld, expected %lld.",
+                    (long long)points_rows, (long long)n_queries);
+  int64_t cells = 0;
+  int rc = check_family(ctx, fam, -1, &cells);
+  if (rc) return rc;
+  if (n_queries == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  ProbParams p{};
+  p.n_vars = fam->n_vars;
+  int off = 0;
+  for (int j = 0; j < fam->n_vars; ++j) {
+    if (!domains[j]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_get_prob_f32: domain %d is NULL", j);
+    p.card[j] = fam->card[j];
+    p.dom[j] = domains[j];
+    p.dom_off[j] = off;
+    off += fam->card[j];
+  }
+  p.dom_total = off;
+  p.n_pa_rows = cells / fam->card[fam->n_vars - 1];
+  long long total = (long long)n_queries * n_values;
+  int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  get_prob_kernel<<<blocks, 256, off * sizeof(float), (cudaStream_t)stream>>>(table, p, points, points_rows, n_values,
+                                                                             query, n_queries, out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+// =========================================================================== ancestral sampling
+namespace {
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct SampleFam {
+  int var;
+  int n_parents;
+  int card;
+  int pad;
+  int parent[CBN_MAX_FAMILY_VARS];
+  int stride[CBN_MAX_FAMILY_VARS];
+  long long cdf_off;
+};
+
+__global__ void __launch_bounds__(256) sample_forward_kernel(int n_vars, const SampleFam* __restrict__ fams,
+                                                             const float* __restrict__ cdf, uint64_t seed,
+                                                             int64_t first, int64_t n, uint8_t* __restrict__ codes,
+                                                             int64_t ld) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint64_t sid = uint64_t(first + i);
+    for (int k = 0; k < n_vars; ++k) {
+      const SampleFam& f = fams[k];
+      long long row = 0;
+      for (int j = 0; j < f.n_parents; ++j) row += (long long)codes[int64_t(f.parent[j]) * ld + i] * f.stride[j];
+      const uint64_t h = splitmix64(splitmix64(seed ^ (sid * 0xD1B54A32D192ED03ull)) + uint64_t(f.var));
+      const float u = float(uint32_t(h >> 40)) * (1.0f / 16777216.0f);
+      const float* c = cdf + f.cdf_off + row * f.card;
+      int x = 0;
+      for (int t = 0; t < f.card - 1; ++t) x += (u >= c[t]);
+      codes[int64_t(f.var) * ld + i] = (uint8_t)x;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cbn_sample_forward(cbn_ctx* ctx, int32_t n_vars, const int32_t* order, const cbn_family* fams,
+                                  const float* cdf, uint64_t seed, int64_t first_sample, int64_t n, uint8_t* codes,
+                                  int64_t ld, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_sample_forward: ctx is NULL");
+  if (n_vars < 1 || !order || !fams || !cdf || !codes || n < 0 || ld < n)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_sample_forward: bad argument");
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<SampleFam> h(n_vars);
+  for (int k = 0; k < n_vars; ++k) {
+    const int v = order[k];
+    if (v < 0 || v >= n_vars) return cbn_fail(ctx, CBN_ERR_INVALID, "order[%d]=%d out of range", k, v);
+    const cbn_family& f = fams[v];
+    int64_t cells = 0;
+    int rc = check_family(ctx, &f, n_vars, &cells);
+    if (rc) return rc;
+    if (f.var[f.n_vars - 1] != v) return cbn_fail(ctx, CBN_ERR_INVALID, "fams[%d] does not end with variable %d", v, v);
+    SampleFam& o = h[k];
+    o.var = v; o.n_parents = f.n_vars - 1; o.card = f.card[f.n_vars - 1]; o.cdf_off = f.table_offset;
+    long long st = 1;
+    for (int j = o.n_parents - 1; j >= 0; --j) {
+      o.parent[j] = f.var[j];
+      o.stride[j] = (int)st;
+      st *= f.card[j];
+    }
+  }
+  SampleFam* d = nullptr;
+  CBN_CUDA(ctx, cudaMallocAsync((void**)&d, sizeof(SampleFam) * n_vars, s));
+  CBN_CUDA(ctx, cudaMemcpyAsync(d, h.data(), sizeof(SampleFam) * n_vars, cudaMemcpyHostToDevice, s));
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8);
+  sample_forward_kernel<<<blocks, 256, 0, s>>>(n_vars, d, cdf, seed, first_sample, n, codes, ld);
+  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, cudaFreeAsync(d, s));
+  return CBN_OK;
+}

@@ -1,0 +1,594 @@
+// Variable elimination: compile-time sum-product contraction (evidence kept symbolic) and the
+// per-row gather/product/normalise executor.  Fills the reference's empty inference plugin
+// slot (cbn/base/inference.py:7-23, cbn/inference/exact.py:13-14) and replaces the
+// mean-and-product loop of BayesianNetwork.infer (cbn/base/bayesian_network.py:243-296).
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+// =========================================================================== contraction
+namespace {
+__global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ cbn_contract d, long long n_out) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
+       o += (long long)gridDim.x * blockDim.x) {
+    long long rem = o;
+    long long base[CBN_MAX_CONTRACT_INPUTS];
+#pragma unroll
+    for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k) base[k] = 0;
+    for (int a = d.n_out_dims - 1; a >= 0; --a) {
+      const int c = (int)(rem % d.out_card[a]);
+      rem /= d.out_card[a];
+#pragma unroll
+      for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+        if (k < d.n_in) base[k] += (long long)c * d.in_stride[k][a];
+    }
+    float acc = 0.0f;
+    for (int s = 0; s < d.sum_card; ++s) {
+      float prod = 1.0f;
+#pragma unroll
+      for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+        if (k < d.n_in) prod *= __ldg(d.in[k] + base[k] + (long long)s * d.sum_stride[k]);
+      acc += prod;
+    }
+    d.out[o] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) normalize_last_kernel(float* x, long long n_rows, int card) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    float* p = x + r * card;
+    float z = 0.0f;
+    for (int t = 0; t < card; ++t) z += p[t];
+    const float inv = z > 0.0f ? 1.0f / z : 0.0f;
+    for (int t = 0; t < card; ++t) p[t] *= inv;
+  }
+}
+}  // namespace
+
+extern "C" int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_factor_contract: ctx is NULL");
+  if (!desc || !desc->out || desc->n_in < 1 || desc->n_in > CBN_MAX_CONTRACT_INPUTS || desc->n_out_dims < 0 ||
+      desc->n_out_dims > CBN_MAX_CONTRACT_DIMS || desc->sum_card < 1)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_factor_contract: bad descriptor");
+  long long n_out = 1;
+  for (int a = 0; a < desc->n_out_dims; ++a) {
+    if (desc->out_card[a] < 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_factor_contract: out_card[%d] < 1", a);
+    n_out *= desc->out_card[a];
+    if (n_out > (1ll << 40)) return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_factor_contract: output too large");
+  }
+  for (int k = 0; k < desc->n_in; ++k)
+    if (!desc->in[k]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_factor_contract: input %d is NULL", k);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = (int)std::min<long long>((n_out + 255) / 256, (long long)ctx->sm_count * 16);
+  contract_kernel<<<blocks, 256, 0, s>>>(*desc, n_out);
+  CBN_CHECK_LAUNCH(ctx);
+  if (desc->normalize_last && desc->n_out_dims > 0) {
+    int card = desc->out_card[desc->n_out_dims - 1];
+    long long rows = n_out / card;
+    int b2 = (int)std::min<long long>((rows + 255) / 256, (long long)ctx->sm_count * 16);
+    normalize_last_kernel<<<b2, 256, 0, s>>>(desc->out, rows, card);
+    CBN_CHECK_LAUNCH(ctx);
+  }
+  return CBN_OK;
+}
+
+// =========================================================================== gather plan
+namespace {
+constexpr int GATHER_TPB = 256;
+constexpr int GATHER_MAX_CT = 8;           // register-resident posterior width; wider targets use the generic kernel
+constexpr int GATHER_MAX_TABLE_EV = CBN_MAX_CONTRACT_DIMS;
+
+struct GTable {                 // device-side table descriptor (kept in shared memory by the kernel)
+  const float* data;
+  int n_cells;
+  int n_ev;
+  int has_target;
+  int smem_off;                 // >= 0: staged copy inside the CTA's shared memory (floats)
+  short slot[GATHER_MAX_TABLE_EV];
+  int stride[GATHER_MAX_TABLE_EV];
+};
+}  // namespace
+
+struct cbn_ve_plan {
+  int device = 0;
+  int n_evidence = 0;
+  int card_t = 0;
+  int n_tables = 0;
+  int normalize = 1;
+  std::vector<int> ev_cards;
+  GTable* d_tables = nullptr;
+  size_t smem_bytes = 0;        // descriptors + staged tables
+  int staged = 0;
+  long long table_bytes = 0;
+};
+
+namespace {
+struct EvPtrs {
+  const float* col[CBN_MAX_EVIDENCE_PTRS];
+  const float* dom[CBN_MAX_EVIDENCE_PTRS];
+  int card[CBN_MAX_EVIDENCE_PTRS];
+};
+
+// codes of 4 consecutive rows of evidence column `slot`, packed little-endian in one word
+struct CodeLoader {
+  const uint8_t* ev;
+  int64_t ld;
+  __device__ __forceinline__ uint32_t load4(int slot, int64_t quad) const {
+    return ld_nc_u32(reinterpret_cast<const uint32_t*>(ev + int64_t(slot) * ld) + quad);
+  }
+};
+struct FloatLoader {
+  const EvPtrs* p;
+  const float* sdom;     // shared-memory copy of the domains, concatenated
+  const int* sdom_off;
+  int64_t n_rows;
+  __device__ __forceinline__ uint32_t load4(int slot, int64_t quad) const {
+    const float* c = p->col[slot] + (quad << 2);
+    const int card = p->card[slot];
+    const float* dm = sdom + sdom_off[slot];
+    uint32_t w = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int code = CBN_UNSEEN;
+      if ((quad << 2) + r < n_rows) code = domain_code(dm, card, __ldg(c + r));
+      w |= uint32_t(code) << (8 * r);
+    }
+    return w;
+  }
+};
+
+template <int CT, typename Loader>
+__device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ sm_tables,
+                                             const Loader& L, int64_t quad, int64_t n_rows, int normalize,
+                                             float* __restrict__ out) {
+  float p[4][CT];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int t = 0; t < CT; ++t) p[r][t] = 1.0f;
+  uint32_t bad = 0;  // one flag byte per row
+  for (int k = 0; k < n_tables; ++k) {
+    const GTable& T = st[k];
+    uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    for (int j = 0; j < T.n_ev; ++j) {
+      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t s = (uint32_t)T.stride[j];
+      const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu, c3 = w >> 24;
+      bad |= (c0 == CBN_UNSEEN ? 1u : 0u) | (c1 == CBN_UNSEEN ? 0x100u : 0u) | (c2 == CBN_UNSEEN ? 0x10000u : 0u) |
+             (c3 == CBN_UNSEEN ? 0x1000000u : 0u);
+      i0 += c0 * s; i1 += c1 * s; i2 += c2 * s; i3 += c3 * s;
+    }
+    const uint32_t lim = (uint32_t)T.n_cells - (T.has_target ? CT : 1);
+    i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
+    const float* base = T.smem_off >= 0 ? sm_tables + T.smem_off : T.data;
+    const uint32_t idx[4] = {i0, i1, i2, i3};
+    if (T.has_target) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float* src = base + idx[r];
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] *= src[t];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float s = base[idx[r]];
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] *= s;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool rb = (bad >> (8 * r)) & 0xffu;
+    float inv = 1.0f;
+    if (normalize) {
+      float z = 0.0f;
+#pragma unroll
+      for (int t = 0; t < CT; ++t) z += p[r][t];
+      inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
+    }
+    if (rb) inv = 0.0f;
+#pragma unroll
+    for (int t = 0; t < CT; ++t) p[r][t] = rb ? 0.0f : p[r][t] * inv;
+  }
+  const int64_t row0 = quad << 2;
+  float* dst = out + row0 * CT;
+  if (row0 + 4 <= n_rows) {
+    // 4 rows * CT floats are contiguous and 16-byte aligned: CT 128-bit stores
+    const float* flat = &p[0][0];
+#pragma unroll
+    for (int v = 0; v < CT; ++v)
+      st_na_f128(reinterpret_cast<float4*>(dst) + v, make_float4(flat[4 * v], flat[4 * v + 1], flat[4 * v + 2], flat[4 * v + 3]));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (row0 + r < n_rows)
+#pragma unroll
+        for (int t = 0; t < CT; ++t) dst[r * CT + t] = p[r][t];
+  }
+}
+
+// shared memory layout: [GTable x n_tables][staged tables (floats)]
+__device__ __forceinline__ const float* stage_plan(const GTable* __restrict__ g_tables, int n_tables, unsigned char* smem,
+                                                   GTable** st_out) {
+  GTable* st = reinterpret_cast<GTable*>(smem);
+  for (int i = threadIdx.x; i < n_tables * int(sizeof(GTable) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(st)[i] = reinterpret_cast<const uint32_t*>(g_tables)[i];
+  __syncthreads();
+  float* sm_tables = reinterpret_cast<float*>(smem + ((size_t(n_tables) * sizeof(GTable) + 15) & ~size_t(15)));
+  for (int k = 0; k < n_tables; ++k) {
+    if (st[k].smem_off >= 0) {
+      const float* src = st[k].data;
+      float* dstp = sm_tables + st[k].smem_off;
+      for (int i = threadIdx.x; i < st[k].n_cells; i += blockDim.x) dstp[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  *st_out = st;
+  return sm_tables;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(GATHER_TPB) gather_codes_kernel(const GTable* __restrict__ g_tables, int n_tables,
+                                                                  const uint8_t* __restrict__ ev, int64_t ld,
+                                                                  int64_t n_rows, int normalize,
+                                                                  float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GTable* st;
+  const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
+  CodeLoader L{ev, ld};
+  const int64_t nquads = (n_rows + 3) >> 2;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
+    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, normalize, out);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const GTable* __restrict__ g_tables, int n_tables,
+                                                                const __grid_constant__ EvPtrs evp, int n_evidence,
+                                                                int64_t n_rows, int normalize,
+                                                                float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int sdom_off[CBN_MAX_EVIDENCE_PTRS];
+  // domains sit at the very end of the dynamic allocation (host adds the room)
+  GTable* st;
+  const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
+  // locate the domain pool after descriptors + staged tables
+  int staged = 0;
+  for (int k = 0; k < n_tables; ++k)
+    if (st[k].smem_off >= 0) staged = max(staged, st[k].smem_off + st[k].n_cells);
+  float* sdom = const_cast<float*>(sm_tables) + ((staged + 3) & ~3);
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int e = 0; e < n_evidence; ++e) { sdom_off[e] = off; off += evp.card[e]; }
+  }
+  __syncthreads();
+  for (int e = 0; e < n_evidence; ++e)
+    for (int i = threadIdx.x; i < evp.card[e]; i += blockDim.x) sdom[sdom_off[e] + i] = evp.dom[e][i];
+  __syncthreads();
+  FloatLoader L{&evp, sdom, sdom_off, n_rows};
+  const int64_t nquads = (n_rows + 3) >> 2;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
+    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, normalize, out);
+}
+
+// wide targets (card_t > GATHER_MAX_CT): one thread per row, posterior accumulated in the output row
+__global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTable* __restrict__ g_tables, int n_tables,
+                                                                       const uint8_t* __restrict__ ev, int64_t ld,
+                                                                       int64_t n_rows, int card_t, int normalize,
+                                                                       float* __restrict__ out) {
+  for (int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
+       row += int64_t(gridDim.x) * blockDim.x) {
+    float* dst = out + row * card_t;
+    for (int t = 0; t < card_t; ++t) dst[t] = 1.0f;
+    bool bad = false;
+    for (int k = 0; k < n_tables; ++k) {
+      const GTable& T = g_tables[k];
+      uint32_t idx = 0;
+      for (int j = 0; j < T.n_ev; ++j) {
+        uint32_t c = ev[int64_t(T.slot[j]) * ld + row];
+        bad |= (c == CBN_UNSEEN);
+        idx += c * (uint32_t)T.stride[j];
+      }
+      idx = min(idx, (uint32_t)T.n_cells - (T.has_target ? card_t : 1));
+      if (T.has_target) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
+      else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] *= s; }
+    }
+    float inv = 1.0f;
+    if (normalize) {
+      float z = 0.0f;
+      for (int t = 0; t < card_t; ++t) z += dst[t];
+      inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
+    }
+    if (bad) inv = 0.0f;
+    for (int t = 0; t < card_t; ++t) dst[t] = bad ? 0.0f : dst[t] * inv;
+  }
+}
+}  // namespace
+
+extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
+                                         const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
+                                         cbn_ve_plan** out) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: ctx is NULL");
+  if (!out || n_evidence < 0 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD || !tables ||
+      n_tables < 1 || n_tables > CBN_MAX_GATHER_TABLES)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: bad argument");
+  DeviceGuard g(ctx->device);
+  std::vector<GTable> h(n_tables);
+  long long total_cells = 0;
+  for (int k = 0; k < n_tables; ++k) {
+    const cbn_gather_table& t = tables[k];
+    if (!t.data || t.n_ev < 0 || t.n_ev > GATHER_MAX_TABLE_EV || t.n_cells < 1 || t.n_cells > 0x7fffffffll)
+      return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: bad descriptor", k);
+    long long need = t.has_target ? card_t : 1;
+    for (int j = 0; j < t.n_ev; ++j) {
+      if (t.ev_slot[j] < 0 || t.ev_slot[j] >= n_evidence)
+        return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: evidence slot %d out of range", k, t.ev_slot[j]);
+      need += (long long)(ev_cards[t.ev_slot[j]] - 1) * t.ev_stride[j];
+      h[k].slot[j] = (short)t.ev_slot[j];
+      h[k].stride[j] = t.ev_stride[j];
+    }
+    if (need > t.n_cells) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: strides address %lld cells, table has %lld", k, need, (long long)t.n_cells);
+    if (t.has_target && !is_aligned(t.data, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: data must be 16-byte aligned", k);
+    h[k].data = t.data; h[k].n_cells = (int)t.n_cells; h[k].n_ev = t.n_ev; h[k].has_target = t.has_target ? 1 : 0;
+    h[k].smem_off = -1;
+    total_cells += t.n_cells;
+  }
+  // stage tables in shared memory when all of them fit comfortably (two CTAs per SM keep their own copy)
+  const size_t desc_bytes = (size_t(n_tables) * sizeof(GTable) + 15) & ~size_t(15);
+  const size_t stage_budget = 64 * 1024;
+  int staged = 0;
+  size_t smem = desc_bytes;
+  if (size_t(total_cells) * 4 <= stage_budget) {
+    int off = 0;
+    for (int k = 0; k < n_tables; ++k) { h[k].smem_off = off; off += (h[k].n_cells + 3) & ~3; }
+    smem += size_t(off) * 4;
+    staged = 1;
+  }
+  cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
+  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
+  p->device = ctx->device; p->n_evidence = n_evidence; p->card_t = card_t; p->n_tables = n_tables;
+  p->normalize = normalize ? 1 : 0; p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
+  p->smem_bytes = smem; p->staged = staged; p->table_bytes = total_cells * 4;
+  cudaError_t e = cudaMalloc((void**)&p->d_tables, sizeof(GTable) * n_tables);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, h.data(), sizeof(GTable) * n_tables, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cbn_ve_plan_destroy(p);
+    return cbn_fail(ctx, CBN_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return CBN_OK;
+}
+
+extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  if (p->d_tables) cudaFree(p->d_tables);
+  delete p;
+}
+
+namespace {
+template <int CT>
+int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, float* out,
+                 cudaStream_t s) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_codes_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int64_t nquads = (n_rows + 3) >> 2;
+  int blocks = (int)std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
+  gather_codes_kernel<CT><<<blocks, GATHER_TPB, p->smem_bytes, s>>>(p->d_tables, p->n_tables, ev, ld, n_rows, p->normalize, out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+template <int CT>
+int launch_f32(cbn_ctx* ctx, const cbn_ve_plan* p, const EvPtrs& evp, size_t dom_floats, int64_t n_rows, float* out,
+               cudaStream_t s) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_f32_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int64_t nquads = (n_rows + 3) >> 2;
+  int blocks = (int)std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
+  size_t smem = p->smem_bytes + 16 + dom_floats * 4;
+  gather_f32_kernel<CT><<<blocks, GATHER_TPB, smem, s>>>(p->d_tables, p->n_tables, evp, p->n_evidence, n_rows, p->normalize, out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+}  // namespace
+
+static int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
+                             float* posterior, cudaStream_t s) {
+  switch (plan->card_t) {
+    case 1: return launch_codes<1>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 2: return launch_codes<2>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 3: return launch_codes<3>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 4: return launch_codes<4>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 5: return launch_codes<5>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 6: return launch_codes<6>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 7: return launch_codes<7>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 8: return launch_codes<8>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    default: {
+      int blocks = (int)std::min<int64_t>((n_rows + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
+      gather_codes_wide_kernel<<<blocks, GATHER_TPB, 0, s>>>(plan->d_tables, plan->n_tables, ev_codes, ld, n_rows,
+                                                             plan->card_t, plan->normalize, posterior);
+      CBN_CHECK_LAUNCH(ctx);
+      return CBN_OK;
+    }
+  }
+}
+
+extern "C" int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
+                                int64_t n_rows, float* posterior, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes: ctx is NULL");
+  if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: bad argument");
+  if (plan->n_evidence > 0 && (ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base");
+  if (!is_aligned(posterior, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: posterior must be 16-byte aligned");
+  if (n_rows == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, posterior, (cudaStream_t)stream);
+}
+
+extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols,
+                              const float* const* domains, int64_t n_rows, float* posterior, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_f32: ctx is NULL");
+  if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && (!ev_cols || !domains)))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: bad argument");
+  if (plan->n_evidence > CBN_MAX_EVIDENCE_PTRS)
+    return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: more than %d evidence columns; encode them and use cbn_ve_run_codes", CBN_MAX_EVIDENCE_PTRS);
+  if (plan->card_t > GATHER_MAX_CT)
+    return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: target cardinality %d > %d; encode and use cbn_ve_run_codes", plan->card_t, GATHER_MAX_CT);
+  if (!is_aligned(posterior, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: posterior must be 16-byte aligned");
+  if (n_rows == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  EvPtrs evp{};
+  size_t dom_floats = 0;
+  for (int e = 0; e < plan->n_evidence; ++e) {
+    if (!ev_cols[e] || !domains[e]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: evidence column %d is NULL", e);
+    evp.col[e] = ev_cols[e]; evp.dom[e] = domains[e]; evp.card[e] = plan->ev_cards[e];
+    dom_floats += plan->ev_cards[e];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (plan->card_t) {
+    case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 2: return launch_f32<2>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 3: return launch_f32<3>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 4: return launch_f32<4>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 5: return launch_f32<5>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 6: return launch_f32<6>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 7: return launch_f32<7>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    default: return launch_f32<8>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+  }
+}
+
+// ---- host-buffer entry point: chunked, double-buffered H2D -> gather -> D2H -----------------------
+static int ensure_io(cbn_ctx* ctx, size_t in_bytes, size_t out_bytes) {
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->io_stream[i]) CBN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_stream[i], cudaStreamNonBlocking));
+    if (!ctx->io_event[i]) CBN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->io_event[i], cudaEventDisableTiming));
+  }
+  if (in_bytes > ctx->io_in_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->io_dev_in[i]) cudaFree(ctx->io_dev_in[i]);
+      if (ctx->io_pin_in[i]) cudaFreeHost(ctx->io_pin_in[i]);
+      ctx->io_dev_in[i] = nullptr; ctx->io_pin_in[i] = nullptr;
+      CBN_CUDA(ctx, cudaMalloc(&ctx->io_dev_in[i], in_bytes));
+      CBN_CUDA(ctx, cudaMallocHost(&ctx->io_pin_in[i], in_bytes));
+    }
+    ctx->io_in_bytes = in_bytes;
+  }
+  if (out_bytes > ctx->io_out_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->io_dev_out[i]) cudaFree(ctx->io_dev_out[i]);
+      if (ctx->io_pin_out[i]) cudaFreeHost(ctx->io_pin_out[i]);
+      ctx->io_dev_out[i] = nullptr; ctx->io_pin_out[i] = nullptr;
+      CBN_CUDA(ctx, cudaMalloc(&ctx->io_dev_out[i], out_bytes));
+      CBN_CUDA(ctx, cudaMallocHost(&ctx->io_pin_out[i], out_bytes));
+    }
+    ctx->io_out_bytes = out_bytes;
+  }
+  return CBN_OK;
+}
+
+extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                     int64_t n_rows, float* posterior_host) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
+  if (!plan || !posterior_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
+  if (n_rows == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  const int64_t chunk = 1 << 20;  // rows per chunk
+  const int ne = std::max(plan->n_evidence, 1);
+  int rc = ensure_io(ctx, size_t(chunk) * ne, size_t(chunk) * plan->card_t * sizeof(float));
+  if (rc) return rc;
+  // Pageable or pinned caller memory: cudaMemcpyAsync handles both; pinned callers get true overlap.
+  cudaPointerAttributes attr{};
+  bool in_pinned = cudaPointerGetAttributes(&attr, ev_codes_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  bool out_pinned = cudaPointerGetAttributes(&attr, posterior_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  int64_t pending_row[2] = {-1, -1}, pending_m[2] = {0, 0};
+  int b = 0;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, b ^= 1) {
+    const int64_t m = std::min(chunk, n_rows - r0);
+    cudaStream_t s = ctx->io_stream[b];
+    // buffer b is free once its previous D2H has been consumed
+    if (pending_row[b] >= 0) {
+      CBN_CUDA(ctx, cudaStreamSynchronize(s));
+      if (!out_pinned)
+        memcpy(posterior_host + pending_row[b] * plan->card_t, ctx->io_pin_out[b], size_t(pending_m[b]) * plan->card_t * sizeof(float));
+      pending_row[b] = -1;
+    }
+    uint8_t* din = (uint8_t*)ctx->io_dev_in[b];
+    for (int e = 0; e < plan->n_evidence; ++e) {
+      const uint8_t* src = ev_codes_host + int64_t(e) * ld + r0;
+      if (in_pinned) {
+        CBN_CUDA(ctx, cudaMemcpyAsync(din + int64_t(e) * chunk, src, m, cudaMemcpyHostToDevice, s));
+      } else {
+        memcpy((uint8_t*)ctx->io_pin_in[b] + int64_t(e) * chunk, src, m);
+      }
+    }
+    if (!in_pinned && plan->n_evidence > 0)
+      CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], size_t(chunk) * plan->n_evidence, cudaMemcpyHostToDevice, s));
+    rc = ve_run_codes_impl(ctx, plan, din, chunk, m, (float*)ctx->io_dev_out[b], s);
+    if (rc) return rc;
+    float* dst = out_pinned ? posterior_host + r0 * plan->card_t : (float*)ctx->io_pin_out[b];
+    CBN_CUDA(ctx, cudaMemcpyAsync(dst, ctx->io_dev_out[b], size_t(m) * plan->card_t * sizeof(float), cudaMemcpyDeviceToHost, s));
+    pending_row[b] = r0; pending_m[b] = m;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (pending_row[i] >= 0) {
+      CBN_CUDA(ctx, cudaStreamSynchronize(ctx->io_stream[i]));
+      if (!out_pinned)
+        memcpy(posterior_host + pending_row[i] * plan->card_t, ctx->io_pin_out[i], size_t(pending_m[i]) * plan->card_t * sizeof(float));
+    }
+  }
+  return CBN_OK;
+}
+
+// =========================================================================== reference scaling
+namespace {
+__global__ void __launch_bounds__(256) batch_max_kernel(const float* __restrict__ x, int64_t n, float* max_out) {
+  float m = 0.0f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    m = fmaxf(m, x[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // probabilities are non-negative: the int ordering of the bit patterns equals the float ordering
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(m));
+}
+__global__ void __launch_bounds__(256) scale_by_inv_kernel(float* x, int64_t n, const float* denom) {
+  const float d = *denom;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    x[i] = __fdiv_rn(x[i], d);
+}
+}  // namespace
+
+extern "C" int cbn_batch_max(cbn_ctx* ctx, const float* x, int64_t n, float* max_out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_batch_max: ctx is NULL");
+  if (!x || !max_out || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_batch_max: bad argument");
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8);
+  batch_max_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, max_out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+extern "C" int cbn_scale_by_inv(cbn_ctx* ctx, float* x, int64_t n, const float* denom, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_scale_by_inv: ctx is NULL");
+  if (!x || !denom || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_scale_by_inv: bad argument");
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8);
+  scale_by_inv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, denom);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}

@@ -1,0 +1,65 @@
+"""Exact inference by Variable Elimination -- the first real occupant of the reference's
+empty plugin slot (cbn/inference/exact.py:6-17, registered in cbn/inference/__init__.py:3
+and selected by the ``inference_obj: exact`` config key, cbn/conf/inference/exact.yaml:1)."""
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from ..base.inference import BaseInference
+from ..ve import QueryPlan, VECompiler
+
+
+class ExactInference(BaseInference):
+    def __init__(self, config: Dict, **kwargs):
+        super(ExactInference, self).__init__(config=config, **kwargs)
+        self.normalization = "row"
+        self.compiler: Optional[VECompiler] = None
+        self._setup_model(config, **kwargs)
+
+    def _setup_model(self, config: Dict, **kwargs):
+        self.normalization = (config or {}).get("normalization", "row")
+        if self.normalization not in ("row", "global_max"):
+            raise ValueError(f"normalization must be 'row' or 'global_max', got {self.normalization!r}")
+        self._budget = {k: int(config[k]) for k in ("table_budget_cells", "merge_budget_cells") if config and k in config}
+
+    def bind(self, tables):
+        """Attach the fitted network tables (called by BayesianNetwork after every fit)."""
+        self.tables = tables
+        self.compiler = VECompiler(tables, **self._budget)
+
+    def plan(self, target_node: str, evidence_names: Sequence[str], do: Sequence[str] = ()) -> QueryPlan:
+        assert self.compiler is not None, "inference engine is not bound to a fitted network"
+        return self.compiler.compile(target_node, list(evidence_names), do=do)
+
+    def _infer(self, target_node: str, evidence: Dict[str, torch.Tensor], do=None, **kwargs) -> torch.Tensor:
+        """Posterior ``P(target | evidence)`` per row: float32 [n_queries, card(target)] on the device.
+
+        evidence: name -> tensor [n_queries, 1] (or [n_queries]) of category VALUES (float), as the
+        reference's ``infer`` takes them (bayesian_network.py:208-226)."""
+        t = self.tables
+        evidence = evidence or {}
+        names = [n for n in evidence.keys() if n != target_node]
+        for n in names:
+            if n not in t.index:
+                raise ValueError(f"evidence variable {n} is not a node of the network")
+        plan = self.plan(target_node, names, do=do or ())
+        if names:
+            nq = int(evidence[names[0]].shape[0])
+            cols = []
+            for n in names:
+                c = evidence[n]
+                if c.shape[0] != nq:
+                    raise ValueError("n_queries must be equal for all features.")
+                cols.append(c.to(t.device, torch.float32, non_blocking=True).reshape(-1).contiguous())
+        else:
+            nq, cols = 1, []
+        out = plan.run_f32(cols, nq)
+        norm = kwargs.get("normalization", self.normalization)
+        if norm == "global_max":
+            from .. import _native as N
+
+            m = torch.zeros(1, dtype=torch.float32, device=t.device)
+            s = N.stream_ptr(t.device)
+            N.check(N.lib().cbn_batch_max(t.ctx.handle, out.data_ptr(), out.numel(), m.data_ptr(), s), t.ctx.handle)
+            N.check(N.lib().cbn_scale_by_inv(t.ctx.handle, out.data_ptr(), out.numel(), m.data_ptr(), s), t.ctx.handle)
+        return out

@@ -1,0 +1,226 @@
+"""Device-resident discrete network: domains, integer codes, count tables, CPTs.
+
+This is the host-side owner of the buffers the C ABI works on.  It replaces the
+per-node ``torch.unique`` fitting of the reference with ONE pass over a code
+matrix for all families (``BayesianNetwork._train`` -> ``Node.fit`` ->
+``BruteForce._fit``; reference cbn/base/bayesian_network.py:138-160,
+cbn/base/node.py:45-110, cbn/parameter_learning/brute_force.py:17-53).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class DiscreteTables:
+    """Variables ``names`` with ``parents[name]`` (sorted by name, as the reference sorts
+    them: bayesian_network.py:104-106).  Family of v = ``parents[v] + [v]``; its dense
+    table is row-major over that list, node fastest."""
+
+    def __init__(self, names: Sequence[str], parents: Dict[str, Sequence[str]], device="cuda"):
+        self.ctx = N.context_for(device)
+        self.device = torch.device("cuda", self.ctx.device_index)
+        self.names: List[str] = list(names)
+        self.index: Dict[str, int] = {n: i for i, n in enumerate(self.names)}
+        self.parents: Dict[str, List[str]] = {n: list(parents.get(n, [])) for n in self.names}
+        for n, ps in self.parents.items():
+            if len(ps) + 1 > N.MAX_FAMILY_VARS:
+                raise ValueError(f"node {n} has {len(ps)} parents; at most {N.MAX_FAMILY_VARS - 1} are supported")
+        self.domains: List[Optional[torch.Tensor]] = [None] * len(self.names)   # float32 [card], sorted
+        self.cards: List[int] = [0] * len(self.names)
+        self.n_total = 0
+        self.fams = None
+        self.offsets: List[int] = []
+        self.n_cells: List[int] = []
+        self.total_cells = 0
+        self.counts: Optional[torch.Tensor] = None   # int64 [total_cells]
+        self.joint: Optional[torch.Tensor] = None    # float32 [total_cells]
+        self.cond: Optional[torch.Tensor] = None     # float32 [total_cells]
+        self._count_plan = None
+
+    # ------------------------------------------------------------------ layout
+    def set_domains(self, domains: Sequence[torch.Tensor]):
+        """Fix the per-variable sorted domains (float32 tensors) and lay out the tables."""
+        assert len(domains) == len(self.names)
+        self.domains = [d.to(self.device, torch.float32).contiguous() for d in domains]
+        self.cards = [int(d.numel()) for d in self.domains]
+        for n, c in zip(self.names, self.cards):
+            if not 1 <= c <= N.MAX_CARD:
+                raise ValueError(f"variable {n} has {c} distinct values; the discrete path supports 1..{N.MAX_CARD}")
+        self._layout()
+
+    def set_cards(self, cards: Sequence[int]):
+        """Integer-coded variables (synthetic workloads): domain of v is 0..card-1."""
+        self.set_domains([torch.arange(int(c), dtype=torch.float32) for c in cards])
+
+    def _layout(self):
+        self._destroy_plan()
+        fams = (N.Family * len(self.names))()
+        self.offsets, self.n_cells = [], []
+        off = 0
+        for i, n in enumerate(self.names):
+            vs = [self.index[p] for p in self.parents[n]] + [i]
+            cs = [self.cards[v] for v in vs]
+            cells = 1
+            for c in cs:
+                cells *= c
+            if cells > 1 << 31:
+                raise ValueError(f"family table of {n} has {cells} cells (> 2^31)")
+            fams[i] = N.make_family(vs, cs, off)
+            self.offsets.append(off)
+            self.n_cells.append(cells)
+            off += _round_up(cells, 4)      # keep every table 16-byte aligned as float32
+        self.fams = fams
+        self.total_cells = off
+        self.counts = torch.zeros(off, dtype=torch.int64, device=self.device)
+        self.joint = None
+        self.cond = None
+        self.n_total = 0
+
+    def _destroy_plan(self):
+        if self._count_plan is not None:
+            N.lib().cbn_count_plan_destroy(self._count_plan)
+            self._count_plan = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def family_vars(self, name: str) -> List[int]:
+        return [self.index[p] for p in self.parents[name]] + [self.index[name]]
+
+    def table_view(self, which: torch.Tensor, name: str) -> torch.Tensor:
+        i = self.index[name]
+        shape = [self.cards[v] for v in self.family_vars(name)]
+        return which[self.offsets[i]: self.offsets[i] + self.n_cells[i]].view(*shape)
+
+    # ------------------------------------------------------------------ ingestion
+    def discover_domain(self, col: torch.Tensor) -> torch.Tensor:
+        """Sorted distinct values of a float32 device column (Node.fit's torch.unique, node.py:85)."""
+        col = col.to(self.device, torch.float32).contiguous()
+        dom = torch.empty(256, dtype=torch.float32, device=self.device)
+        card = torch.empty(1, dtype=torch.int32, device=self.device)
+        N.check(N.lib().cbn_domain_f32(self.ctx.handle, col.data_ptr(), col.numel(), dom.data_ptr(), card.data_ptr(),
+                                       N.stream_ptr(self.device)), self.ctx.handle)
+        c = int(card.item())
+        if c < 0:
+            raise ValueError(
+                f"column has more than {N.MAX_CARD} distinct values; it is not a discrete variable for the "
+                "brute-force estimator")
+        return dom[:c].clone()
+
+    def encode(self, col: torch.Tensor, var: int, out: torch.Tensor, unseen: Optional[torch.Tensor] = None):
+        col = col.to(self.device, torch.float32).contiguous()
+        N.check(N.lib().cbn_encode_f32(self.ctx.handle, col.data_ptr(), col.numel(), self.domains[var].data_ptr(),
+                                       self.cards[var], out.data_ptr(), unseen.data_ptr() if unseen is not None else None,
+                                       N.stream_ptr(self.device)), self.ctx.handle)
+
+    def new_code_matrix(self, n: int) -> torch.Tensor:
+        ld = _round_up(max(n, 1), 16)
+        return torch.empty((len(self.names), ld), dtype=torch.uint8, device=self.device)
+
+    def encode_columns(self, cols: Dict[str, torch.Tensor], strict: bool = True) -> torch.Tensor:
+        n = int(next(iter(cols.values())).numel())
+        codes = self.new_code_matrix(n)
+        unseen = torch.zeros(1, dtype=torch.int64, device=self.device)
+        for name in self.names:
+            self.encode(cols[name].reshape(-1), self.index[name], codes[self.index[name]], unseen)
+        if strict and int(unseen.item()) != 0:
+            raise ValueError(f"{int(unseen.item())} values are not in the fitted domains")
+        return codes
+
+    # ------------------------------------------------------------------ counting
+    def count(self, codes: torch.Tensor, n: int):
+        """Accumulate the family counts of ``n`` samples (columns of ``codes``: uint8 [n_vars, ld])."""
+        assert codes.dtype == torch.uint8 and codes.dim() == 2 and codes.shape[0] == len(self.names)
+        assert codes.stride(1) == 1
+        lib = N.lib()
+        if self._count_plan is None:
+            h = C.c_void_p()
+            N.check(lib.cbn_count_plan_create(self.ctx.handle, self.fams, len(self.names), len(self.names), C.byref(h)),
+                    self.ctx.handle)
+            self._count_plan = h
+        N.check(lib.cbn_count_run(self.ctx.handle, self._count_plan, codes.data_ptr(), codes.stride(0), int(n),
+                                  self.counts.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
+        self.n_total += int(n)
+
+    def count_groups(self) -> int:
+        return N.lib().cbn_count_plan_groups(self._count_plan) if self._count_plan is not None else 0
+
+    def finalize(self):
+        """counts -> joint (fp32(c)/fp32(n)) and cond (joint / (parent + 1e-10))."""
+        if self.n_total < 1:
+            raise ValueError("no samples counted")
+        self.joint = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
+        self.cond = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
+        N.check(N.lib().cbn_cpt_from_counts(self.ctx.handle, self.counts.data_ptr(), self.fams, len(self.names),
+                                            self.n_total, self.joint.data_ptr(), self.cond.data_ptr(),
+                                            N.stream_ptr(self.device)), self.ctx.handle)
+
+    def set_cond_tables(self, cpts: Sequence):
+        """Install ground-truth conditional tables (synthetic workloads; no counting)."""
+        self.cond = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
+        for i, t in enumerate(cpts):
+            t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+            assert t.numel() == self.n_cells[i]
+            self.cond[self.offsets[i]: self.offsets[i] + self.n_cells[i]] = t.to(self.device)
+
+    def fit_columns(self, cols: Dict[str, torch.Tensor]):
+        """Full fit from float32 columns: domains, codes, counts, CPTs."""
+        doms = [self.discover_domain(cols[n].reshape(-1)) for n in self.names]
+        self.set_domains(doms)
+        codes = self.encode_columns(cols)
+        n = int(next(iter(cols.values())).numel())
+        self.count(codes, n)
+        self.finalize()
+        return codes
+
+    # ------------------------------------------------------------------ reference views
+    def mle_tensor(self, name: str) -> torch.Tensor:
+        """The reference's sparse ``mle_tensor`` [M, P+2] of one family (brute_force.py:45-53)."""
+        i = self.index[name]
+        vs = self.family_vars(name)
+        out = torch.empty((self.n_cells[i], len(vs) + 1), dtype=torch.float32, device=self.device)
+        rows = torch.zeros(1, dtype=torch.int64, device=self.device)
+        doms = N.ptr_array([self.domains[v].data_ptr() for v in vs])
+        fam = N.make_family(list(range(len(vs))), [self.cards[v] for v in vs], 0)
+        N.check(N.lib().cbn_mle_from_counts(self.ctx.handle, self.counts[self.offsets[i]:].data_ptr(), C.byref(fam), doms,
+                                            self.n_total, out.data_ptr(), rows.data_ptr(), N.stream_ptr(self.device)),
+                self.ctx.handle)
+        return out[: int(rows.item())].clone()
+
+    def get_prob(self, name: str, points: torch.Tensor, query: Optional[torch.Tensor]) -> torch.Tensor:
+        """``P(x = points[q, v] | parents = query[q])`` (BruteForce._get_prob, brute_force.py:172-244)."""
+        i = self.index[name]
+        vs = self.family_vars(name)
+        points = points.to(self.device, torch.float32).contiguous()
+        assert points.dim() == 2
+        fam = N.make_family(list(range(len(vs))), [self.cards[v] for v in vs], 0)
+        doms = N.ptr_array([self.domains[v].data_ptr() for v in vs])
+        if query is None:
+            table = self.joint[self.offsets[i]:]
+            nq = points.shape[0]
+            qptr = None
+        else:
+            assert query.dim() == 3 and query.shape[-1] == 1, f"Query must be [n_queries, n_parents, 1]. Got {tuple(query.shape)}."
+            if query.shape[1] != len(vs) - 1:
+                raise ValueError(f"query has {query.shape[1]} parent columns, node {name} has {len(vs) - 1} parents")
+            query = query.to(self.device, torch.float32).contiguous()
+            table = self.cond[self.offsets[i]:]
+            nq = query.shape[0]
+            qptr = query.data_ptr()
+        out = torch.empty((nq, points.shape[1]), dtype=torch.float32, device=self.device)
+        N.check(N.lib().cbn_get_prob_f32(self.ctx.handle, table.data_ptr(), C.byref(fam), doms, points.data_ptr(),
+                                         points.shape[0], points.shape[1], qptr, nq, out.data_ptr(),
+                                         N.stream_ptr(self.device)), self.ctx.handle)
+        return out

@@ -1,0 +1,403 @@
+"""Variable-elimination compiler: (target, evidence set) -> gather plan.
+
+The reference has no working VE (cbn/inference/exact.py:13-14 is ``pass``; its
+``BayesianNetwork.infer``, cbn/base/bayesian_network.py:208-305, is a posterior only
+for star DAGs -- SURVEY.md section 3.3).  This module is the engine behind the reference's
+empty inference plugin slot.
+
+Idea (SURVEY.md section 7 "hard parts"): the evidence *pattern* is fixed for a batch, so the
+hidden variables are eliminated ONCE, on the GPU, with the evidence variables kept as
+free axes of the factors ("evidence-symbolic" elimination).  What is left is a handful
+of tables over (evidence subset, target); each query row only gathers one slice per
+table, multiplies and normalises -- an HBM-bound kernel (``cbn_ve_run_*``).
+
+Host work here is graph logic only (pruning, ordering, stride bookkeeping); every
+floating-point operation runs in ``cbn_factor_contract`` on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+class PlanTooLarge(NotImplementedError):
+    pass
+
+
+@dataclass
+class Factor:
+    scope: List[int]                     # variable ids; tensor is row-major over this list
+    tensor: Optional[torch.Tensor]       # float32 device tensor (None in dry-run)
+
+    def size(self, cards) -> int:
+        s = 1
+        for v in self.scope:
+            s *= cards[v]
+        return s
+
+
+@dataclass
+class PlanStats:
+    n_relevant: int = 0
+    n_hidden: int = 0
+    n_steps: int = 0
+    max_table_cells: int = 0
+    contraction_madds: int = 0
+    final_tables: List[Tuple[Tuple[int, ...], int]] = field(default_factory=list)
+    support_unchecked: bool = False
+    relevant_evidence: List[int] = field(default_factory=list)
+
+
+class QueryPlan:
+    """A compiled (target, evidence-set) query.  Owns the final tables and the native plan."""
+
+    def __init__(self, tables_owner, target: int, evidence: List[int], card_t: int, finals: List[Factor],
+                 normalize: bool, stats: PlanStats):
+        self.owner = tables_owner
+        self.ctx = tables_owner.ctx
+        self.device = tables_owner.device
+        self.target = target
+        self.evidence = list(evidence)
+        self.card_t = card_t
+        self.finals = finals
+        self.normalize = normalize
+        self.stats = stats
+        self.handle = None
+        cards = tables_owner.cards
+        slot = {v: i for i, v in enumerate(self.evidence)}
+        arr = (N.GatherTable * len(finals))()
+        for k, f in enumerate(finals):
+            has_t = bool(f.scope) and f.scope[-1] == target
+            ev_scope = f.scope[:-1] if has_t else f.scope
+            g = arr[k]
+            g.data = f.tensor.data_ptr()
+            g.n_cells = f.tensor.numel()
+            g.n_ev = len(ev_scope)
+            g.has_target = 1 if has_t else 0
+            stride = card_t if has_t else 1
+            for j in range(len(ev_scope) - 1, -1, -1):
+                g.ev_slot[j] = slot[ev_scope[j]]
+                g.ev_stride[j] = stride
+                stride *= cards[ev_scope[j]]
+        ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
+        h = C.c_void_p()
+        N.check(N.lib().cbn_ve_plan_create_gather(self.ctx.handle, len(self.evidence), ev_cards, card_t, arr, len(finals),
+                                                  1 if normalize else 0, C.byref(h)), self.ctx.handle)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                N.lib().cbn_ve_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # bytes the kernel must move per row: relevant evidence codes in, posterior out
+    def algorithmic_bytes_per_row(self) -> int:
+        return len(self.stats.relevant_evidence) + 4 * self.card_t
+
+    def run_codes(self, ev_codes: torch.Tensor, n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ev_codes: uint8 [len(evidence), ld] on the device (row e = evidence variable e of the plan)."""
+        assert ev_codes.dtype == torch.uint8 and ev_codes.is_cuda
+        if out is None:
+            out = torch.empty((n_rows, self.card_t), dtype=torch.float32, device=self.device)
+        ld = ev_codes.stride(0) if ev_codes.dim() == 2 else 0
+        N.check(N.lib().cbn_ve_run_codes(self.ctx.handle, self.handle, ev_codes.data_ptr(), ld, int(n_rows),
+                                         out.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
+        return out
+
+    def run_f32(self, ev_cols: Sequence[torch.Tensor], n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ev_cols[e]: float32 device column of evidence variable e (the reference's [nq,1] tensors)."""
+        if out is None:
+            out = torch.empty((n_rows, self.card_t), dtype=torch.float32, device=self.device)
+        cols = N.ptr_array([c.data_ptr() for c in ev_cols])
+        doms = N.ptr_array([self.owner.domains[v].data_ptr() for v in self.evidence])
+        N.check(N.lib().cbn_ve_run_f32(self.ctx.handle, self.handle, cols, doms, int(n_rows), out.data_ptr(),
+                                       N.stream_ptr(self.device)), self.ctx.handle)
+        return out
+
+    def run_codes_host(self, ev_codes_host: torch.Tensor, n_rows: int, out_host: torch.Tensor) -> torch.Tensor:
+        """Host buffers in, host buffer out (copies inside; synchronous)."""
+        assert not ev_codes_host.is_cuda and not out_host.is_cuda
+        N.check(N.lib().cbn_ve_run_codes_host(self.ctx.handle, self.handle, ev_codes_host.data_ptr(),
+                                              ev_codes_host.stride(0), int(n_rows), out_host.data_ptr()), self.ctx.handle)
+        return out_host
+
+
+class VECompiler:
+    """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
+
+    def __init__(self, tables, table_budget_cells: int = 1 << 28, merge_budget_cells: int = 1 << 24,
+                 check_support: bool = True):
+        self.t = tables
+        self.table_budget = int(table_budget_cells)
+        self.merge_budget = int(merge_budget_cells)
+        self.check_support = check_support
+        self._cache: Dict[tuple, QueryPlan] = {}
+        self._has_zero: Dict[int, bool] = {}
+
+    # ---------------------------------------------------------------- graph helpers
+    def _parents(self, v: int) -> List[int]:
+        return self.t.family_vars(self.t.names[v])[:-1]
+
+    def _ancestors(self, seeds, cut=()) -> set:
+        """Ancestors of ``seeds`` (inclusive); the parents of variables in ``cut`` (interventions) are not followed."""
+        seen, stack = set(), list(seeds)
+        while stack:
+            v = stack.pop()
+            if v in seen:
+                continue
+            seen.add(v)
+            if v not in cut:
+                stack.extend(self._parents(v))
+        return seen
+
+    def _cond_has_zero(self, v: int) -> bool:
+        if v not in self._has_zero:
+            view = self.t.table_view(self.t.cond, self.t.names[v])
+            self._has_zero[v] = bool((view == 0).any().item())
+        return self._has_zero[v]
+
+    # ---------------------------------------------------------------- device contraction
+    def _contract(self, inputs: List[Factor], out_scope: List[int], sum_var: Optional[int], dry: bool,
+                  normalize_last: bool = False) -> Factor:
+        cards = self.t.cards
+        if dry:
+            return Factor(out_scope, None)
+        if len(out_scope) > N.MAX_CONTRACT_DIMS:
+            raise PlanTooLarge(f"factor with {len(out_scope)} axes exceeds {N.MAX_CONTRACT_DIMS}")
+        d = N.Contract()
+        d.n_out_dims = len(out_scope)
+        for a, v in enumerate(out_scope):
+            d.out_card[a] = cards[v]
+        d.sum_card = cards[sum_var] if sum_var is not None else 1
+        d.n_in = len(inputs)
+        for k, f in enumerate(inputs):
+            strides = {}
+            s = 1
+            for v in reversed(f.scope):
+                strides[v] = s
+                s *= cards[v]
+            d.inp[k] = f.tensor.data_ptr()
+            for a, v in enumerate(out_scope):
+                d.in_stride[k][a] = strides.get(v, 0)
+            d.sum_stride[k] = strides.get(sum_var, 0) if sum_var is not None else 0
+        n_out = 1
+        for v in out_scope:
+            n_out *= cards[v]
+        out = torch.empty(max(n_out, 1), dtype=torch.float32, device=self.t.device)
+        d.out = out.data_ptr()
+        d.normalize_last = 1 if normalize_last else 0
+        N.check(N.lib().cbn_factor_contract(self.t.ctx.handle, C.byref(d), N.stream_ptr(self.t.device)), self.t.ctx.handle)
+        return Factor(out_scope, out)
+
+    # ---------------------------------------------------------------- compile
+    def compile(self, target: str, evidence: Sequence[str], do: Sequence[str] = (), dry: bool = False):
+        """``do``: evidence variables that are set by intervention (graph surgery: their own CPT is dropped
+        and their parents are cut off) -- the reference's ``infer(do=...)`` is a TODO (bayesian_network.py:229-232)."""
+        t = self.t
+        cards = t.cards
+        T = t.index[target]
+        E = [t.index[e] for e in evidence if e != target]      # evidence on the target itself is not forwarded
+        D = set()                                               # (bayesian_network.py:190-196)
+        for d in do or ():
+            if d not in evidence:
+                raise ValueError(f"do-variable {d} needs a value: pass it in the evidence dict as well")
+            if d == target:
+                raise ValueError("cannot intervene on the target node")
+            D.add(t.index[d])
+        key = (T, tuple(E), tuple(sorted(D)))
+        if not dry and key in self._cache:
+            return self._cache[key]
+        Eset = set(E)
+        order_key = {v: i for i, v in enumerate(E)}
+        stats = PlanStats()
+
+        def sort_scope(scope) -> List[int]:
+            # evidence axes (plan order) first, then hidden, target last (fastest)
+            return sorted(set(scope), key=lambda v: (2 if v == T else (0 if v in Eset else 1), order_key.get(v, v)))
+
+        relevant = self._ancestors([T] + E, cut=D)
+        stats.n_relevant = len(relevant)
+        factors: List[Factor] = []
+        for v in sorted(relevant):
+            if v in D:
+                continue
+            scope = t.family_vars(t.names[v])
+            tensor = None if dry else t.table_view(t.cond, t.names[v]).reshape(-1)
+            factors.append(Factor(list(scope), tensor))
+        hidden = [v for v in relevant if v not in Eset and v != T]
+        stats.n_hidden = len(hidden)
+
+        # connected components of the non-evidence variables (evidence instantiation cuts the graph)
+        parent = {v: v for v in hidden + [T]}
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        for f in factors:
+            free = [v for v in f.scope if v not in Eset]
+            for a, b in zip(free, free[1:]):
+                parent[find(a)] = find(b)
+        comp_t = find(T)
+        in_t = lambda f: any(v not in Eset and find(v) == comp_t for v in f.scope)
+        main = [f for f in factors if in_t(f)]
+        rest = [f for f in factors if not in_t(f)]
+        rel_ev = set()
+        for f in main:
+            rel_ev |= {v for v in f.scope if v in Eset}
+        stats.relevant_evidence = [v for v in E if v in rel_ev]
+
+        finals = self._eliminate(main, [v for v in hidden if find(v) == comp_t], sort_scope, stats, dry, T)
+
+        # support of the dropped part: a row whose (irrelevant) evidence has probability zero is all zeros in
+        # the oracle's convention; only factors that can be zero matter
+        if self.check_support and rest:
+            if dry:
+                stats.support_unchecked = True
+            else:
+                groups: Dict[int, List[Factor]] = {}
+                consts: List[Factor] = []
+                for f in rest:
+                    free = [v for v in f.scope if v not in Eset]
+                    (groups.setdefault(find(free[0]), []) if free else consts).append(f)
+                # a constant (all-evidence) factor is a scalar table indexed by its own evidence axes
+                for f in consts:
+                    v = f.scope[-1]
+                    if self._cond_has_zero(v):
+                        finals.append(self._contract([f], sort_scope(f.scope), None, dry))
+                for root, fs in groups.items():
+                    owners = [f.scope[-1] for f in fs]
+                    if not any(self._cond_has_zero(v) for v in owners):
+                        continue
+                    try:
+                        sub = PlanStats()
+                        res = self._eliminate(fs, [v for v in hidden if find(v) == root], sort_scope, sub, dry, T)
+                        stats.contraction_madds += sub.contraction_madds
+                        for r in res:
+                            if bool((r.tensor == 0).any().item()):
+                                finals.append(r)
+                    except PlanTooLarge:
+                        stats.support_unchecked = True
+
+        finals = self._merge_finals(finals, sort_scope, stats, dry, T)
+        stats.final_tables = [(tuple(f.scope), f.size(cards)) for f in finals]
+        if dry:
+            return stats
+        # a single pre-normalised target table needs no arithmetic per row
+        normalize = True
+        with_t = [f for f in finals if f.scope and f.scope[-1] == T]
+        if len(finals) == 1 and len(with_t) == 1:
+            finals = [self._contract(finals, finals[0].scope, None, dry, normalize_last=True)]
+            normalize = False
+        if not with_t:
+            # target independent of everything kept (cannot happen: P(T|pa) always mentions T)
+            raise RuntimeError("internal: no final factor mentions the target")
+        plan = QueryPlan(t, T, E, cards[T], finals, normalize, stats)
+        self._cache[key] = plan
+        return plan
+
+    def _eliminate(self, factors: List[Factor], hidden: List[int], sort_scope, stats: PlanStats, dry: bool, T: int):
+        cards = self.t.cards
+        factors = list(factors)
+        hidden = list(hidden)
+
+        def cells(scope):
+            s = 1
+            for v in scope:
+                s *= cards[v]
+            return s
+
+        while hidden:
+            best, best_cost, best_scope = None, None, None
+            for v in hidden:
+                scope = set()
+                for f in factors:
+                    if v in f.scope:
+                        scope |= set(f.scope)
+                scope.discard(v)
+                c = cells(scope)
+                if best_cost is None or c < best_cost:
+                    best, best_cost, best_scope = v, c, scope
+            if best_cost > self.table_budget:
+                raise PlanTooLarge(
+                    f"eliminating the cheapest hidden variable needs a table of {best_cost} cells "
+                    f"(budget {self.table_budget}); this query needs the per-row executor")
+            v = best
+            hidden.remove(v)
+            touching = [f for f in factors if v in f.scope]
+            factors = [f for f in factors if v not in f.scope]
+            # the kernel multiplies at most MAX_CONTRACT_INPUTS factors at once: pre-multiply the smallest ones
+            while len(touching) > N.MAX_CONTRACT_INPUTS:
+                touching.sort(key=lambda f: f.size(cards))
+                a, b = touching[0], touching[1]
+                sc = sort_scope(a.scope + b.scope)
+                if cells(sc) > self.table_budget:
+                    raise PlanTooLarge("pre-multiplication exceeds the table budget")
+                stats.contraction_madds += 2 * cells(sc)
+                touching = touching[2:] + [self._contract([a, b], sc, None, dry)]
+            out_scope = sort_scope(best_scope)
+            stats.n_steps += 1
+            stats.max_table_cells = max(stats.max_table_cells, best_cost)
+            stats.contraction_madds += best_cost * cards[v] * len(touching)
+            factors.append(self._contract(touching, out_scope, v, dry))
+        return factors
+
+    def _merge_finals(self, finals: List[Factor], sort_scope, stats: PlanStats, dry: bool, T: int) -> List[Factor]:
+        """Multiply final tables together while the product stays within the merge budget: fewer gathers
+        per row, and a single table can be normalised at compile time."""
+        cards = self.t.cards
+        finals = [Factor(sort_scope(f.scope), f.tensor) if f.scope == sort_scope(f.scope) else
+                  self._contract([f], sort_scope(f.scope), None, dry) for f in finals]
+
+        def cells(scope):
+            s = 1
+            for v in scope:
+                s *= cards[v]
+            return s
+
+        while len(finals) > 1:
+            best = None
+            for i in range(len(finals)):
+                for j in range(i + 1, len(finals)):
+                    sc = sort_scope(finals[i].scope + finals[j].scope)
+                    c = cells(sc)
+                    if best is None or c < best[0]:
+                        best = (c, i, j, sc)
+            c, i, j, sc = best
+            if c > self.merge_budget and len(finals) <= N.MAX_GATHER_TABLES:
+                break
+            if c > self.table_budget:
+                raise PlanTooLarge("cannot reduce the number of final tables within the budget")
+            a, b = finals[i], finals[j]
+            finals = [f for k, f in enumerate(finals) if k not in (i, j)]
+            stats.contraction_madds += 2 * c
+            stats.max_table_cells = max(stats.max_table_cells, c)
+            finals.append(self._contract([a, b], sc, None, dry))
+        return finals
+
+
+class DryTables:
+    """Structure-only stand-in for ``DiscreteTables`` (no device): lets the planner be
+    exercised on a CPU-only machine with ``compile(..., dry=True)``."""
+
+    def __init__(self, names, cards, parents_by_name):
+        self.names = list(names)
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.cards = [int(c) for c in cards]
+        self.parents = {n: list(parents_by_name.get(n, [])) for n in self.names}
+        self.cond = None
+        self.device = None
+        self.ctx = None
+
+    def family_vars(self, name):
+        return [self.index[p] for p in self.parents[name]] + [self.index[name]]

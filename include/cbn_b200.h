@@ -1,0 +1,214 @@
+/* cbn_b200.h -- C ABI of the B200-native engine for the cbn discrete hot path.
+ *
+ * The reference (Giovannibriglia/ContinuousBayesianNetwork) is pure Python and has
+ * no FFI; its boundary for this path is the Python plugin API.  Each entry point
+ * below names the reference routine whose arithmetic it replaces (file:line under
+ * the reference tree).  The Python host mirror of the plugin API
+ * (continuousbayesiannetwork_b200/) binds these with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative cbn_status otherwise, and
+ *     leaves a message retrievable with cbn_last_error(ctx);
+ *   - no exceptions, no torch types: plain pointers and sizes;
+ *   - device buffers are caller-owned (the Python host allocates them with torch);
+ *     the library owns only the opaque ctx / plan handles and their small
+ *     descriptor uploads;
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void*); nothing
+ *     synchronises the device unless stated;
+ *   - one ctx per device, one caller thread per ctx.
+ *
+ * Data layout
+ *   - samples / evidence are integer codes, uint8, structure-of-arrays: column c
+ *     of a code matrix lives at `codes + c * ld` (ld = leading dimension in
+ *     bytes, a multiple of 16; base pointer 16-byte aligned).  Code k means "the
+ *     k-th value of the variable's sorted domain"; CBN_UNSEEN marks a value that
+ *     is not in the domain;
+ *   - a family is [parents (sorted-name order) ..., node]; its dense table is
+ *     row-major over that list, node fastest -- the lexicographic row order of the
+ *     reference's torch.unique(dim=0) (cbn/parameter_learning/brute_force.py:42);
+ *   - count tables are int64, concatenated, family f starting at
+ *     fams[f].table_offset.
+ */
+#ifndef CBN_B200_H
+#define CBN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CBN_API __attribute__((visibility("default")))
+#else
+#define CBN_API
+#endif
+
+#define CBN_ABI_VERSION 1
+#define CBN_MAX_FAMILY_VARS 12
+#define CBN_MAX_CARD 255
+#define CBN_UNSEEN 255
+#define CBN_MAX_CONTRACT_DIMS 24
+#define CBN_MAX_CONTRACT_INPUTS 16
+#define CBN_MAX_GATHER_TABLES 16
+#define CBN_MAX_EVIDENCE_PTRS 64
+
+typedef enum cbn_status {
+  CBN_OK = 0,
+  CBN_ERR_INVALID = -1,   /* bad argument (the reference raises ValueError / assert) */
+  CBN_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  CBN_ERR_NOMEM = -3,
+  CBN_ERR_UNSUPPORTED = -4
+} cbn_status;
+
+typedef struct cbn_ctx cbn_ctx;
+typedef struct cbn_count_plan cbn_count_plan;
+typedef struct cbn_ve_plan cbn_ve_plan;
+typedef void* cbn_stream; /* cudaStream_t */
+
+typedef struct cbn_family {
+  int32_t n_vars;                    /* parents + 1 */
+  int32_t var[CBN_MAX_FAMILY_VARS];  /* column ids, node last */
+  int32_t card[CBN_MAX_FAMILY_VARS];
+  int64_t table_offset;              /* first cell in the concatenated tables */
+} cbn_family;
+
+/* ---- context ------------------------------------------------------------------ */
+CBN_API int cbn_abi_version(void);
+CBN_API int cbn_ctx_create(int device, cbn_ctx** out);
+CBN_API void cbn_ctx_destroy(cbn_ctx* ctx);
+CBN_API const char* cbn_last_error(cbn_ctx* ctx); /* ctx may be NULL: last error of this thread */
+CBN_API int cbn_device_sm_count(cbn_ctx* ctx);
+
+/* ---- ingestion: float categories -> codes ---------------------------------------
+ * Replaces the float-equality keying of BruteForce (brute_force.py:42, :228) and the
+ * per-column pandas->list->numpy->torch round trip of BayesianNetwork._train
+ * (cbn/base/bayesian_network.py:144-157).
+ *
+ * cbn_domain_f32: sorted distinct values of a column (Node.fit's torch.unique,
+ * cbn/base/node.py:85-110).  domain_out: device float[256]; card_out: device int32
+ * (set to -1 if the column has more than CBN_MAX_CARD distinct values).
+ * cbn_encode_f32: exact-match search of every value in the sorted domain.
+ * n_unseen (device, may be NULL) is incremented by the number of values not found. */
+CBN_API int cbn_domain_f32(cbn_ctx* ctx, const float* col, int64_t n, float* domain_out, int32_t* card_out,
+                   cbn_stream stream);
+CBN_API int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const float* sorted_domain, int32_t card,
+                   uint8_t* codes_out, unsigned long long* n_unseen, cbn_stream stream);
+
+/* ---- CPT counting -----------------------------------------------------------------
+ * Replaces the sort-based torch.unique(dim=0, return_counts=True) of
+ * BruteForce._fit (brute_force.py:17-53) for every family of the network in ONE
+ * pass over the code matrix: privatised shared-memory histograms, flushed into the
+ * caller's int64 tables with atomic adds (so repeated calls ACCUMULATE: that is the
+ * sharded / incremental fit; zero the tables first for a fresh fit).
+ * A sample whose family index falls outside the table (an CBN_UNSEEN code) is
+ * skipped for that family. */
+CBN_API int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t n_fams, int32_t n_cols,
+                          cbn_count_plan** out);
+CBN_API void cbn_count_plan_destroy(cbn_count_plan* plan);
+CBN_API int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
+                  unsigned long long* counts, cbn_stream stream);
+/* introspection for the bench: number of family groups (kernel passes over the tile) */
+CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
+
+/* ---- tables -> probabilities --------------------------------------------------------
+ * joint[cell] = fp32(count) / fp32(n_total)                     (brute_force.py:43)
+ * cond[pa, x] = joint[pa, x] / (sum_x' joint[pa, x'] + 1e-10)   (brute_force.py:228-241)
+ * Either output may be NULL.  IEEE fp32 division; unseen parent rows give zeros. */
+CBN_API int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const cbn_family* fams, int32_t n_fams,
+                        long long n_total, float* joint, float* cond, cbn_stream stream);
+
+/* The reference's sparse `mle_tensor` (brute_force.py:45-53) of ONE family: rows
+ * [pa_1..pa_P, x, prob] for the non-zero cells, in lexicographic order.
+ * counts: that family's table (already offset).  domains: host array of n_vars device
+ * pointers to the sorted domains.  mle_out: device float[n_cells * (n_vars+1)]
+ * (capacity); n_rows_out: device int64. */
+CBN_API int cbn_mle_from_counts(cbn_ctx* ctx, const long long* counts, const cbn_family* fam,
+                        const float* const* domains, long long n_total, float* mle_out,
+                        long long* n_rows_out, cbn_stream stream);
+
+/* BruteForce._get_prob (brute_force.py:172-244) without the broadcast join:
+ * out[q, v] = cond[pa(query[q]), code(points[q, v])], 0 if any value is unseen.
+ * points: float[Q, V]; query: float[Q, P] (NULL for the marginal branch :192-201,
+ * where `table` must be the JOINT table and the parents are summed out).
+ * points_rows == 1 broadcasts one row of candidate values to every query. */
+CBN_API int cbn_get_prob_f32(cbn_ctx* ctx, const float* table, const cbn_family* fam, const float* const* domains,
+                     const float* points, int64_t points_rows, int32_t n_values, const float* query,
+                     int64_t n_queries, float* out, cbn_stream stream);
+
+/* ---- variable elimination -------------------------------------------------------------
+ * The reference has no working VE (cbn/inference/exact.py:13-14 is `pass`;
+ * BayesianNetwork.infer, cbn/base/bayesian_network.py:208-305, is correct only for
+ * star DAGs).  These entry points are what its empty inference plugin slot
+ * (cbn/base/inference.py:7-23) binds.
+ *
+ * cbn_factor_contract: one sum-product step of the compile-time (evidence-symbolic)
+ * elimination:  out[o] = sum_{s < sum_card} prod_k in_k[ o . stride_k + s * sum_stride_k ].
+ * `o` ranges over the row-major grid out_card[0..n_out_dims). */
+typedef struct cbn_contract {
+  int32_t n_out_dims;
+  int32_t out_card[CBN_MAX_CONTRACT_DIMS];
+  int32_t sum_card; /* 1 = plain product */
+  int32_t n_in;
+  const float* in[CBN_MAX_CONTRACT_INPUTS];
+  int32_t in_stride[CBN_MAX_CONTRACT_INPUTS][CBN_MAX_CONTRACT_DIMS];
+  int32_t sum_stride[CBN_MAX_CONTRACT_INPUTS];
+  float* out;
+  int32_t normalize_last; /* 1: divide every slice over the LAST out dim by its sum (0 if the sum is 0) */
+} cbn_contract;
+CBN_API int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stream stream);
+
+/* A compiled query: after the hidden variables have been eliminated once with the
+ * evidence variables kept as free axes, every row only gathers
+ *     post[row, t] ~ prod_k table_k[ sum_j code[row, ev_k_j] * ev_stride_k_j + t ]
+ * and normalises over t.  Tables have the target as their fastest axis (stride 1,
+ * extent card_t).  ev_slot indexes the evidence columns handed to cbn_ve_run_*. */
+typedef struct cbn_gather_table {
+  const float* data; /* device */
+  int64_t n_cells;
+  int32_t n_ev;
+  int32_t ev_slot[CBN_MAX_CONTRACT_DIMS];
+  int32_t ev_stride[CBN_MAX_CONTRACT_DIMS];
+  int32_t has_target; /* 0: a per-row scalar (support mask) */
+} cbn_gather_table;
+
+CBN_API int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
+                              const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
+                              cbn_ve_plan** out);
+CBN_API void cbn_ve_plan_destroy(cbn_ve_plan* plan);
+
+/* evidence as codes: column e of the plan's evidence list at ev_codes + e * ld.
+ * posterior: device float[n_rows, card_t], rows sum to 1 (all zeros when the evidence
+ * has probability 0 or contains CBN_UNSEEN). */
+CBN_API int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
+                     int64_t n_rows, float* posterior, cbn_stream stream);
+/* evidence as the reference hands it over: one float column per evidence variable
+ * (infer's Dict[str, Tensor[nq,1]], bayesian_network.py:208-226), encoded on the fly
+ * against the sorted domains.  ev_cols / domains: host arrays of device pointers. */
+CBN_API int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols,
+                   const float* const* domains, int64_t n_rows, float* posterior, cbn_stream stream);
+/* same as cbn_ve_run_codes but with HOST buffers (pinned or pageable): chunks are
+ * copied in, processed and copied out on internal streams, double-buffered.
+ * Synchronous: returns when `posterior_host` is complete. */
+CBN_API int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                          int64_t n_rows, float* posterior_host);
+
+/* reference scaling: BayesianNetwork.infer divides the whole batch by ONE global max
+ * (bayesian_network.py:296).  max_out: device float (caller zero-initialises). */
+CBN_API int cbn_batch_max(cbn_ctx* ctx, const float* x, int64_t n, float* max_out, cbn_stream stream);
+CBN_API int cbn_scale_by_inv(cbn_ctx* ctx, float* x, int64_t n, const float* denom, cbn_stream stream);
+
+/* ---- ancestral sampling (synthetic workloads; BruteForce._sample's network analogue,
+ * brute_force.py:246-265).  Counter-based: sample i of variable v depends only on
+ * (seed, first_sample + i, v), so any sharding of the sample range yields the same data.
+ * order: topological order of the n_vars variables; cdf: concatenated cumulative
+ * conditional tables (same layout as cond), cdf_offset[v] its start. */
+CBN_API int cbn_sample_forward(cbn_ctx* ctx, int32_t n_vars, const int32_t* order, const cbn_family* fams,
+                       const float* cdf, uint64_t seed, int64_t first_sample, int64_t n, uint8_t* codes,
+                       int64_t ld, cbn_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBN_B200_H */

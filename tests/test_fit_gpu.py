@@ -1,0 +1,204 @@
+"""GPU parity: CPT fitting path (encode, count, normalise, mle rows, lookups) against the oracle
+and the golden vectors produced by the live reference.  Integer results are bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CFG = {"estimator_name": "brute_force"}
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_frozen_lake_estimator_matches_reference(golden_dir):
+    from continuousbayesiannetwork_b200.utils import choose_probability_estimator
+
+    g = _load(golden_dir, "frozen_lake.npz")
+    d = torch.tensor(g["data"], device=DEV)
+    obs, act, rew = d[:, 0], d[:, 1], d[:, 2]
+    est = choose_probability_estimator("brute_force", CFG, device=DEV)
+    est.fit(rew, torch.stack([act, obs]))
+    assert est.mle_tensor.shape == (44, 4)
+    assert np.array_equal(est.mle_tensor.cpu().numpy(), g["mle_reward"])          # bit-exact rows + probs
+    t = est.tables
+    counts = t.table_view(t.counts, "__node__").cpu().numpy()
+    assert counts.sum() == 10000
+    assert np.array_equal(counts[counts > 0], O.mle_counts(torch.tensor(g["mle_reward"]), 10000))
+    # get_prob on every training row and on the 100x100 grid of the reference's test script
+    pts = torch.tensor(g["domain_reward"], device=DEV).unsqueeze(0).expand(d.shape[0], -1)
+    got = est.get_prob(pts, d[:, [1, 0]].unsqueeze(-1)).cpu().numpy()
+    np.testing.assert_allclose(got, g["getprob_rows"], rtol=1e-6, atol=0)
+    est2 = choose_probability_estimator("brute_force", CFG, device=DEV)
+    est2.fit(rew, torch.stack([obs, act]))
+    assert np.array_equal(est2.mle_tensor.cpu().numpy(), g["mle_reward_obs_action"])
+    grid = torch.tensor(g["grid_query"], device=DEV)
+    pts = torch.tensor(g["domain_reward"], device=DEV).unsqueeze(0).expand(grid.shape[0], -1)
+    got = est2.get_prob(pts, grid.unsqueeze(-1)).cpu().numpy()
+    np.testing.assert_allclose(got, g["getprob_grid"], rtol=1e-6, atol=0)
+    # argmax map of the reference's test (tests/test_frozen_lake_parameter_learning.py:41-55)
+    assert np.array_equal(got.argmax(1), g["getprob_grid"].argmax(1))
+    # marginal branch
+    est3 = choose_probability_estimator("brute_force", CFG, device=DEV)
+    est3.fit(rew, None)
+    assert np.array_equal(est3.mle_tensor.cpu().numpy(), g["mle_reward_marginal"])
+    got = est3.get_prob(torch.tensor(g["getprob_marginal_reward_pts"], device=DEV)).cpu().numpy()
+    np.testing.assert_allclose(got, g["getprob_marginal_reward"], rtol=1e-6, atol=0)
+
+
+def test_synthetic_families_match_reference(golden_dir):
+    from continuousbayesiannetwork_b200.parameter_learning import BruteForce
+
+    g = _load(golden_dir, "synthetic_families.npz")
+    for ci in range(int(g["n_cases"])):
+        node = torch.tensor(g[f"c{ci}_node"], device=DEV)
+        parents = torch.tensor(g[f"c{ci}_parents"], device=DEV) if f"c{ci}_parents" in g else None
+        est = BruteForce(CFG, device=DEV)
+        est.fit(node, parents)
+        assert np.array_equal(est.mle_tensor.cpu().numpy(), g[f"c{ci}_mle"]), ci
+        pts = torch.tensor(g[f"c{ci}_pts"], device=DEV)
+        if parents is not None:
+            got = est.get_prob(pts, torch.tensor(g[f"c{ci}_query"], device=DEV).unsqueeze(-1))
+        else:
+            got = est.get_prob(pts[:1])
+        np.testing.assert_allclose(got.cpu().numpy(), g[f"c{ci}_getprob"], rtol=1e-6, atol=0, err_msg=str(ci))
+        # sampling draws rows of the empirical joint
+        smp = est.sample(64)
+        rows = {tuple(r) for r in g[f"c{ci}_mle"][:, :-1].tolist()}
+        assert all(tuple(r) in rows for r in smp.cpu().numpy().tolist())
+
+
+def test_estimator_errors_mirror_reference():
+    from continuousbayesiannetwork_b200.parameter_learning import BruteForce
+    from continuousbayesiannetwork_b200.utils import choose_probability_estimator
+
+    with pytest.raises(ValueError):
+        choose_probability_estimator("no_such_estimator", CFG)
+    est = BruteForce(CFG, device=DEV)
+    with pytest.raises(AssertionError):
+        est.get_prob(torch.zeros(1, 2, device=DEV))
+    x = torch.tensor([0.0, 1, 1, 0, 1], device=DEV)
+    est.fit(x, torch.stack([x, 1 - x]))
+    with pytest.raises(ValueError):
+        est.get_prob(torch.zeros(3, 2, device=DEV), torch.zeros(2, 2, 1, device=DEV))
+    with pytest.raises(AssertionError):
+        est.get_prob(torch.zeros(2, 2, device=DEV), torch.zeros(2, 2, device=DEV))
+    with pytest.raises(RuntimeError):
+        BruteForce(CFG, device="cpu").fit(x.cpu(), None)       # no CPU path
+    with pytest.raises(ValueError):                              # > 255 distinct values is not discrete
+        BruteForce(CFG, device=DEV).fit(torch.arange(1000, device=DEV, dtype=torch.float32), None)
+
+
+def test_domain_and_encode_kernels():
+    from continuousbayesiannetwork_b200.tables import DiscreteTables
+
+    rng = np.random.default_rng(0)
+    for card, n in ((1, 5), (2, 1), (7, 1003), (255, 200_001)):
+        dom = np.sort(rng.choice(np.arange(-500, 500) * 0.125, size=card, replace=False)).astype(np.float32)
+        if card > 3:
+            dom[0] = -0.0
+            dom = np.unique(dom)
+            card = len(dom)
+        col = dom[rng.integers(0, card, size=n)]
+        t = DiscreteTables(["a"], {}, device=DEV)
+        got = t.discover_domain(torch.tensor(col, device=DEV)).cpu().numpy()
+        assert np.array_equal(got, np.unique(col)), card
+        t.set_domains([torch.tensor(np.unique(col))])
+        # unaligned views take the scalar path, aligned ones the 128-bit path: same codes
+        for off in (0, 1, 3):
+            src = torch.tensor(np.concatenate([np.zeros(off, np.float32), col]), device=DEV)[off:]
+            out = torch.full((n + 16,), 77, dtype=torch.uint8, device=DEV)
+            unseen = torch.zeros(1, dtype=torch.int64, device=DEV)
+            t.encode(src, 0, out, unseen)
+            assert np.array_equal(out[:n].cpu().numpy(), np.searchsorted(np.unique(col), col).astype(np.uint8))
+            assert int(unseen.item()) == 0 and int(out[n].item()) == 77
+        bad = torch.tensor(col, device=DEV).clone()
+        bad[::3] = 12345.0
+        out = torch.zeros(n + 16, dtype=torch.uint8, device=DEV)
+        unseen = torch.zeros(1, dtype=torch.int64, device=DEV)
+        t.encode(bad, 0, out, unseen)
+        assert int(unseen.item()) == len(range(0, n, 3)) and bool((out[:n:3] == 255).all())
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1001, 262_147])
+def test_count_kernel_bit_exact_vs_oracle(n):
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+
+    spec = synth.alarm()
+    codes = sample_network(spec, seed=5, first=0, n=n, device=DEV)
+    ref = synth.sample_forward_numpy(spec, 5, 0, n)
+    assert np.array_equal(codes[:, :n].cpu().numpy(), ref)
+    t = tables_from_spec(spec, DEV)
+    t.count(codes, n)
+    t.count(codes, n)                      # calls accumulate
+    for i, name in enumerate(spec.names):
+        want = 2 * O.dense_counts(ref, spec.parents[i] + [i], spec.cards)
+        assert np.array_equal(t.table_view(t.counts, name).cpu().numpy(), want), name
+    t.finalize()
+    for i, name in enumerate(spec.names):
+        cnt = 2 * O.dense_counts(ref, spec.parents[i] + [i], spec.cards)
+        joint, cond = O.cpt_from_counts(cnt, 2 * n)
+        assert np.array_equal(t.table_view(t.joint, name).cpu().numpy(), joint), name       # bit-exact fp32 division
+        np.testing.assert_allclose(t.table_view(t.cond, name).cpu().numpy(), cond, rtol=1e-6, atol=0)
+
+
+def test_count_kernel_grouped_and_large_families():
+    """200-node card-4 network: tables exceed one CTA's shared memory (several family groups); plus a family
+    too large for shared memory at all (global-atomic path).  Checked against the C oracle."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+    from continuousbayesiannetwork_b200.tables import DiscreteTables
+    from oracle.build_oracle import count_families
+
+    spec = synth.random_ktree_dag()
+    n = 1_000_003
+    codes = sample_network(spec, seed=9, first=0, n=n, device=DEV)
+    t = tables_from_spec(spec, DEV)
+    t.count(codes, n)
+    assert t.count_groups() >= 2
+    fams = [spec.parents[i] + [i] for i in range(spec.n)]
+    want = count_families(codes.cpu().numpy(), n, fams, spec.cards)
+    for i, name in enumerate(spec.names):
+        got = t.table_view(t.counts, name).cpu().numpy()
+        assert np.array_equal(got, want[i]), name
+        assert got.sum() == n
+    # marginalisation consistency: summing a family table over the node gives the parents' joint counts
+    i = max(range(spec.n), key=lambda k: len(spec.parents[k]))
+    tab = t.table_view(t.counts, spec.names[i]).cpu().numpy()
+    p0 = spec.parents[i][0]
+    m = np.bincount(codes[p0, :n].cpu().numpy(), minlength=4)
+    assert np.array_equal(tab.sum(axis=tuple(range(1, tab.ndim))), m)
+    # one huge family: 5 parents of card 12 -> 12^6 = 2,985,984 cells (11.9 MB as uint32)
+    rng = np.random.default_rng(1)
+    names = [f"v{i}" for i in range(6)]
+    big = DiscreteTables(names, {"v5": names[:5]}, device=DEV)
+    big.set_cards([12] * 6)
+    m = 300_001
+    raw = rng.integers(0, 12, size=(6, m)).astype(np.uint8)
+    cm = big.new_code_matrix(m)
+    cm[:, :m] = torch.from_numpy(raw).to(DEV)
+    big.count(cm, m)
+    want = count_families(raw, m, [[0, 1, 2, 3, 4, 5]] + [[i] for i in range(5)], [12] * 6)
+    assert np.array_equal(big.table_view(big.counts, "v5").cpu().numpy(), want[0])
+    assert np.array_equal(big.table_view(big.counts, "v2").cpu().numpy(), want[3])
+
+
+def test_unseen_codes_are_skipped_not_corrupting():
+    from continuousbayesiannetwork_b200.tables import DiscreteTables
+
+    t = DiscreteTables(["a", "b"], {"b": ["a"]}, device=DEV)
+    t.set_cards([3, 2])
+    raw = np.array([[0, 1, 255, 2, 2, 1, 0], [1, 0, 1, 255, 1, 1, 0]], dtype=np.uint8)
+    cm = t.new_code_matrix(7)
+    cm.zero_()
+    cm[:, :7] = torch.from_numpy(raw).to(DEV)
+    t.count(cm, 7)
+    assert t.table_view(t.counts, "a").cpu().tolist() == [2, 2, 2]
+    assert t.table_view(t.counts, "b").cpu().tolist() == [[1, 1], [1, 1], [0, 1]]

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: synthetic networks, the sampler's CPU restatement,
+the VE planner (dry run), sharding, and the world_size-2 count allreduce over gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from continuousbayesiannetwork_b200 import sharding, synth
+from continuousbayesiannetwork_b200.ve import DryTables, PlanTooLarge, VECompiler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_networks_have_the_published_shapes():
+    a = synth.asia()
+    assert a.n == 8 and sum(len(p) for p in a.parents) == 8
+    for c in a.cpts:
+        np.testing.assert_allclose(c.sum(axis=-1), 1.0)
+    al = synth.alarm()           # asserts 37 / 46 / 509 inside
+    assert max(len(p) for p in al.parents) == 4 and max(al.cards) == 4
+    assert max(int(np.prod(c.shape)) for c in al.cpts) == 108
+    r = synth.random_ktree_dag()
+    assert r.n == 200 and max(len(p) for p in r.parents) <= 4 and set(r.cards) == {4}
+    L = synth.layered_dag()
+    assert L.n == 1000 and 2 <= min(L.cards) and max(L.cards) <= 8
+    for spec in (a, al, r, L):
+        order = spec.topological_order()
+        pos = {v: i for i, v in enumerate(order)}
+        assert all(pos[p] < pos[i] for i in range(spec.n) for p in spec.parents[i])
+        # parents are in sorted-name order (the reference's CPT axis order)
+        assert all([spec.names[p] for p in ps] == sorted(spec.names[p] for p in ps) for ps in spec.parents)
+
+
+def test_sampler_restatement_is_shard_invariant_and_matches_the_cpts():
+    spec = synth.asia()
+    full = synth.sample_forward_numpy(spec, 11, 0, 40000)
+    parts = np.concatenate([synth.sample_forward_numpy(spec, 11, 0, 15001),
+                            synth.sample_forward_numpy(spec, 11, 15001, 24999)], axis=1)
+    assert np.array_equal(full, parts)
+    assert abs(full[spec.names.index("smoke")].mean() - 0.5) < 0.01
+    either = full[spec.names.index("either")]
+    assert np.array_equal(either, full[spec.names.index("lung")] | full[spec.names.index("tub")])
+
+
+def _dry(spec, target, ev, **kw):
+    return VECompiler(DryTables(spec.names, spec.cards, spec.parents_by_name()), **kw).compile(target, ev, dry=True)
+
+
+def test_planner_asia_and_alarm():
+    a = synth.asia()
+    for t in ("lung", "tub", "bronc"):
+        s = _dry(a, t, ["asia", "smoke", "xray", "dysp"])
+        scope = tuple(a.names.index(e) for e in ["asia", "smoke", "xray", "dysp"]) + (a.names.index(t),)
+        assert s.final_tables == [(scope, 32)]
+        assert len(s.relevant_evidence) == 4 and s.n_hidden == 3
+    al = synth.alarm()
+    for t in synth.ALARM_TARGETS:
+        s = _dry(al, t, synth.ALARM_EVIDENCE)
+        assert s.n_hidden == 24 and len(s.final_tables) == 1
+        assert s.final_tables[0][1] == 839808 * al.cards[al.names.index(t)]
+
+
+def test_planner_prunes_barren_and_d_separated_parts():
+    a = synth.asia()
+    # evidence on smoke only: xray/dysp/either are barren, asia/tub irrelevant
+    s = _dry(a, "lung", ["smoke"])
+    assert s.n_relevant == 2 and s.n_hidden == 0 and s.final_tables == [((2, 3), 4)]
+    # target with no evidence: prior marginal
+    s = _dry(a, "either", [])
+    assert s.relevant_evidence == [] and s.final_tables == [((5,), 2)]
+    # intervention on lung cuts smoke -> lung
+    s = _dry(a, "smoke", ["lung"])
+    assert len(s.relevant_evidence) == 1
+    c = VECompiler(DryTables(a.names, a.cards, a.parents_by_name()))
+    s = c.compile("smoke", ["lung"], do=["lung"], dry=True)
+    assert s.relevant_evidence == []
+    with pytest.raises(ValueError):
+        c.compile("smoke", [], do=["lung"], dry=True)
+
+
+def test_planner_budget_and_layered_stress():
+    r = synth.random_ktree_dag()
+    rng = np.random.default_rng(5)
+    vs = rng.choice(200, size=11, replace=False)
+    s = _dry(r, r.names[vs[0]], [r.names[v] for v in vs[1:]])
+    assert s.max_table_cells <= 1 << 28
+    with pytest.raises(PlanTooLarge):
+        _dry(r, r.names[vs[0]], [r.names[v] for v in vs[1:]], table_budget_cells=1 << 10)
+    L = synth.layered_dag()
+    with pytest.raises(PlanTooLarge):   # treewidth of the 20x50 layered DAG is far beyond exact inference
+        _dry(L, "l16_15", ["l03_10", "l10_20", "l19_01", "l12_40", "l15_15"])
+
+
+def test_shard_ranges_cover_exactly():
+    for n in (0, 1, 7, 1000, 16_777_216 + 5):
+        for w in (1, 2, 3, 8):
+            rs = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            assert max(e - s for s, e in rs) <= (n + w - 1) // w + 15
+            assert all(s % 16 == 0 for s, e in rs if e > s)
+
+
+@pytest.mark.timeout(120)
+def test_count_allreduce_gloo_world2(tmp_path):
+    """Two CPU ranks count disjoint sample shards with the oracle and combine the int64 tables through
+    sharding.allreduce_counts (gloo here, NCCL on the GPUs): the sum equals the single-process tables."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", script, str(tmp_path)],
+                         capture_output=True, text=True, timeout=110, cwd=ROOT)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()

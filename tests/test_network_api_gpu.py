@@ -1,0 +1,159 @@
+"""GPU parity through the reference-facing API: BayesianNetwork / Node / registries, against the golden
+outputs of the live reference (star DAGs with full parent evidence, the only shape where the reference
+is a posterior -- SURVEY.md section 3.3)."""
+import os
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PL = {"estimator_name": "brute_force"}
+INF = {"inference_obj": "exact"}
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _frozen_lake(golden_dir):
+    from continuousbayesiannetwork_b200 import BayesianNetwork
+
+    g = _load(golden_dir, "frozen_lake.npz")
+    df = pd.DataFrame(g["data"], columns=["obs_0", "action", "reward"])
+    dag = nx.DiGraph()
+    dag.add_edges_from([("obs_0", "reward"), ("action", "reward")])
+    return g, df, BayesianNetwork(dag, df, PL, INF, device=DEV)
+
+
+def test_frozen_lake_network_fit_and_infer(golden_dir):
+    g, df, bn = _frozen_lake(golden_dir)
+    for name in ("obs_0", "action", "reward"):
+        node = bn.nodes_obj[name]
+        assert np.array_equal(node.estimator.mle_tensor.cpu().numpy(), g["mle_" + name])
+        assert np.array_equal(node.info[name][3].cpu().numpy(), g["domain_" + name])
+    assert bn.nodes_obj["reward"].parents_names == ["action", "obs_0"]
+    ev = {"obs_0": torch.tensor(g["data"][:, 0:1]), "action": torch.tensor(g["data"][:, 1:2])}
+    # reference scaling: one global max over the batch
+    pdf, dom = bn.infer("reward", ev, N_max=2, normalization="global_max")
+    np.testing.assert_allclose(pdf.cpu().numpy(), g["infer_rows_pdf"], rtol=1e-5, atol=1e-12)
+    assert np.array_equal(dom.cpu().numpy(), g["infer_rows_dom"])
+    # default: rows sum to one == the reference row-normalised
+    pdf, _ = bn.infer("reward", ev, N_max=2)
+    ref = g["infer_rows_pdf"] / g["infer_rows_pdf"].sum(1, keepdims=True)
+    np.testing.assert_allclose(pdf.cpu().numpy(), ref, rtol=1e-5, atol=1e-12)
+    # unseen parent configurations / values -> all-zero rows, as in the reference
+    ev2 = {"obs_0": torch.tensor(g["infer_unseen_obs"]), "action": torch.tensor(g["infer_unseen_act"])}
+    pdf2, _ = bn.infer("reward", ev2, N_max=2, normalization="global_max")
+    np.testing.assert_allclose(pdf2.cpu().numpy(), g["infer_unseen_pdf"], rtol=1e-5, atol=1e-12)
+    # get_pdf with all parents observed == the reference's factor tensor [nq, 1, 1, V]
+    pdfs, tdom, pdom = bn.get_pdf("reward", ev, N_max=2)
+    assert pdfs.shape == (10000, 1, 1, 2) and tdom.shape == (10000, 2) and pdom.shape == (10000, 2, 1)
+    np.testing.assert_allclose(pdfs.reshape(-1, 2).cpu().numpy(), g["getprob_rows"], rtol=1e-6, atol=0)
+    # MAP prediction helper
+    pred = bn.benchmarking_df(df.iloc[:512], "reward", batch_size=200)
+    assert np.array_equal(pred, g["data"][:512, [0, 1, 2]][np.arange(512), 2] * 0 + g["getprob_rows"][:512].argmax(1))
+
+
+def test_true_posterior_where_the_reference_is_not_one(golden_dir):
+    """Only `action` observed: the reference averages P(r|obs,a) uniformly over obs; the
+    engine returns the actual posterior sum_obs P(obs) P(r|obs,a)."""
+    g, df, bn = _frozen_lake(golden_dir)
+    pdf, _ = bn.infer("reward", {"action": torch.tensor([[0.0], [1.0], [2.0], [3.0]])}, N_max=2)
+    d = g["data"]
+    p_obs = np.array([(d[:, 0] == o).mean() for o in g["domain_obs_0"]])
+    for a in range(4):
+        want = np.zeros(2)
+        for oi, o in enumerate(g["domain_obs_0"]):
+            sel = (d[:, 0] == o) & (d[:, 1] == a)
+            if sel.sum():
+                want += p_obs[oi] * np.array([(d[sel, 2] == 0).mean(), (d[sel, 2] == 1).mean()])
+        np.testing.assert_allclose(pdf[a].cpu().numpy(), want / want.sum(), rtol=2e-5)
+    # evidence=None is the prior marginal (the reference raises AttributeError)
+    pdf, dom = bn.infer("reward", None, N_max=2)
+    np.testing.assert_allclose(pdf.cpu().numpy(), [[0.9982, 0.0018]], rtol=1e-5)
+
+
+def test_star_dag_with_unsorted_parents(golden_dir):
+    from continuousbayesiannetwork_b200 import BayesianNetwork
+
+    g = _load(golden_dir, "star_infer.npz")
+    cols = [str(c) for c in g["columns"]]
+    df = pd.DataFrame(g["data"], columns=cols)
+    dag = nx.DiGraph()
+    dag.add_edges_from([(c, "y") for c in cols[:-1]])
+    bn = BayesianNetwork(dag, df, PL, INF, device=DEV)
+    assert np.array_equal(bn.nodes_obj["y"].estimator.mle_tensor.cpu().numpy(), g["mle_y"])
+    ev = {c: torch.tensor(g["ev_" + c]) for c in cols[:-1]}
+    pdf, dom = bn.infer("y", ev, N_max=3, normalization="global_max")
+    np.testing.assert_allclose(pdf.cpu().numpy(), g["infer_pdf"], rtol=1e-5, atol=1e-12)
+    assert np.array_equal(dom.cpu().numpy(), g["infer_dom"])
+    # N_max below the cardinality sub-samples the domain with rounded linspace indices
+    pdf2, dom2 = bn.infer("y", ev, N_max=2, normalization="global_max")
+    assert dom2.shape == (512, 2) and np.array_equal(dom2[0].cpu().numpy(), g["infer_dom"][0][[0, 2]])
+
+
+def test_api_errors_update_and_persistence(golden_dir, tmp_path):
+    from continuousbayesiannetwork_b200 import BayesianNetwork, Node
+
+    g, df, bn = _frozen_lake(golden_dir)
+    cyc = nx.DiGraph()
+    cyc.add_edges_from([("a", "b"), ("b", "a")])
+    with pytest.raises(ValueError):
+        BayesianNetwork(cyc, df, PL, INF, device=DEV)
+    with pytest.raises(ValueError):
+        BayesianNetwork(bn.initial_dag, df, {"estimator_name": "gp_gpytorch"}, INF, device=DEV)
+    with pytest.raises(ValueError):
+        bn.infer("nope", {})
+    with pytest.raises(ValueError):
+        bn.infer("reward", {"ghost": torch.zeros(2, 1)})
+    node = Node("c", "brute_force", PL, ["b", "a"], device=DEV)
+    x = torch.tensor([0.0, 1, 0, 1], device=DEV)
+    with pytest.raises(ValueError):
+        node.fit(x, None)
+    with pytest.raises(ValueError):
+        node.fit(x, torch.stack([x]))
+    node.fit(x, torch.stack([x, 1 - x]))            # rows given in ["b","a"] order, stored sorted
+    assert node.parents_names == ["a", "b"]
+    assert node.estimator.mle_tensor.cpu().tolist() == [[0.0, 1.0, 1.0, 0.5], [1.0, 0.0, 0.0, 0.5]]
+    # update_knowledge replaces (reference) or accumulates (engine extension)
+    half = df.iloc[:5000]
+    bn.update_knowledge(half)
+    assert bn.tables.n_total == 5000
+    bn.update_knowledge(df.iloc[5000:], accumulate=True)
+    assert bn.tables.n_total == 10000
+    assert np.array_equal(bn.nodes_obj["reward"].estimator.mle_tensor.cpu().numpy(), g["mle_reward"])
+    with pytest.raises(ValueError):
+        bn.update_knowledge(pd.DataFrame({"obs_0": [99.0], "action": [0.0], "reward": [0.0]}), accumulate=True)
+    # save / load round trip
+    path = str(tmp_path / "bn.pt")
+    bn.save_model(path)
+    bn2 = BayesianNetwork(bn.initial_dag, df.iloc[:100], PL, INF, device=DEV)
+    bn2.load_model(path)
+    assert np.array_equal(bn2.nodes_obj["reward"].estimator.mle_tensor.cpu().numpy(), g["mle_reward"])
+    p = str(tmp_path / "node.pt")
+    bn.nodes_obj["reward"].save_node(p)
+    bn2.nodes_obj["reward"].load_node(p)
+    assert np.array_equal(bn2.nodes_obj["reward"].estimator.mle_tensor.cpu().numpy(), g["mle_reward"])
+
+
+def test_node_get_prob_partial_evidence_grid(golden_dir):
+    """Factor tensor with an unobserved parent: [nq, N, N, V] on the reference's N-point grids."""
+    g, df, bn = _frozen_lake(golden_dir)
+    node = bn.nodes_obj["reward"]
+    q = {"action": torch.tensor([[1.0], [3.0]], device=DEV)}
+    pdfs, tdom, pdom = node.get_prob(q, N=2)
+    assert pdfs.shape == (2, 2, 2, 2)
+    # parents sorted (action, obs_0); obs_0 grid for N=2 is (min, max) = (0, 14); action repeated
+    mle = {tuple(r[:3]): r[3] for r in g["mle_reward"].tolist()}
+    def cond(a, o, r):
+        den = sum(mle.get((a, o, rr), 0.0) for rr in (0.0, 1.0))
+        return mle.get((a, o, r), 0.0) / (den + 1e-10)
+    for qi, a in enumerate((1.0, 3.0)):
+        for oi, o in enumerate((0.0, 14.0)):
+            for ri, r in enumerate((0.0, 1.0)):
+                assert abs(float(pdfs[qi, 0, oi, ri]) - cond(a, o, r)) < 1e-6
+                assert abs(float(pdfs[qi, 1, oi, ri]) - cond(a, o, r)) < 1e-6

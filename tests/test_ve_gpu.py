@@ -1,0 +1,206 @@
+"""GPU parity: batched Variable Elimination against the fp32 textbook-VE oracle (O2), fp64 full
+enumeration (O3) and -- where the reference itself is a posterior -- the live reference's outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-5          # north_star: posteriors within 1e-5 relative in fp32
+
+
+def _net(spec):
+    return O.DiscreteNet(spec.cards, spec.parents, spec.cpts)
+
+
+def _codes_matrix(ev: np.ndarray) -> torch.Tensor:
+    """[n_rows, n_ev] numpy codes -> uint8 [n_ev, ld] device matrix (ld multiple of 16)."""
+    n, k = ev.shape
+    ld = (n + 15) // 16 * 16
+    m = torch.zeros((max(k, 1), max(ld, 16)), dtype=torch.uint8, device=DEV)
+    if k:
+        m[:, :n] = torch.from_numpy(np.ascontiguousarray(ev.T.astype(np.uint8))).to(DEV)
+    return m
+
+
+def _check(spec, infer, target, ev_names, ev, rtol=RTOL, truth64=True):
+    net = _net(spec)
+    ids = [spec.names.index(e) for e in ev_names]
+    plan = infer.plan(target, ev_names)
+    got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
+    want = O.ve_posterior(net, spec.names.index(target), ids, ev)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-30)
+    if truth64:
+        w64 = O.ve_posterior(net, spec.names.index(target), ids, ev, dtype=torch.float64)
+        np.testing.assert_allclose(got, w64, rtol=rtol, atol=1e-30)
+    assert np.all(np.abs(got.sum(1) - 1) < 1e-5)
+    return plan, got
+
+
+def test_asia_all_evidence_configurations():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.asia()
+    _, infer = install_cpts(spec, DEV)
+    ev_names = ["asia", "smoke", "xray", "dysp"]
+    ev = np.array([[(i >> k) & 1 for k in range(4)] for i in range(16)] * 3)[:45]   # 45 rows: not a multiple of 4
+    for target in ("lung", "tub", "bronc", "either"):
+        plan, got = _check(spec, infer, target, ev_names, ev)
+        truth = O.enumerate_posterior(_net(spec), spec.names.index(target), [spec.names.index(e) for e in ev_names], ev)
+        np.testing.assert_allclose(got, truth, rtol=RTOL, atol=1e-30)
+        assert plan.algorithmic_bytes_per_row() == 4 + 8
+    # other evidence sets, including evidence below / above the target and none at all
+    rng = np.random.default_rng(1)
+    for target, names in (("lung", ["smoke"]), ("smoke", ["lung", "dysp"]), ("either", []), ("asia", ["xray"]),
+                          ("dysp", ["asia", "tub", "smoke", "lung", "bronc", "either", "xray"])):
+        ev = rng.integers(0, 2, size=(33, len(names)))
+        _check(spec, infer, target, names, ev)
+
+
+def test_alarm_and_random_dags():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.alarm()
+    _, infer = install_cpts(spec, DEV)
+    codes = synth.sample_forward_numpy(spec, 21, 0, 2051)
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    for target in synth.ALARM_TARGETS:
+        plan, _ = _check(spec, infer, target, synth.ALARM_EVIDENCE, codes[ids].T)
+        assert plan.stats.final_tables[0][1] == 839808 * spec.cards[spec.names.index(target)]
+    # random evidence patterns on the Alarm structure
+    rng = np.random.default_rng(2)
+    for _ in range(6):
+        vs = rng.choice(spec.n, size=int(rng.integers(2, 9)), replace=False)
+        names = [spec.names[v] for v in vs[1:]]
+        _check(spec, infer, spec.names[vs[0]], names, codes[vs[1:]].T[:257])
+    # partial k-tree, card 3, wide targets excluded
+    spec = synth.random_ktree_dag(n=40, card=3, k=4, max_parents=3, seed=4)
+    _, infer = install_cpts(spec, DEV)
+    codes = synth.sample_forward_numpy(spec, 22, 0, 515)
+    for _ in range(8):
+        vs = rng.choice(spec.n, size=int(rng.integers(1, 8)), replace=False)
+        _check(spec, infer, spec.names[vs[0]], [spec.names[v] for v in vs[1:]], codes[vs[1:]].T)
+
+
+def test_wide_target_and_mixed_cards():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    rng = np.random.default_rng(3)
+    names = ["a", "b", "c", "d", "e"]
+    cards = [3, 11, 2, 5, 7]
+    parents = [[], [0], [0, 1], [1, 2], [3]]
+    cpts = synth._dirichlet_cpts(rng, cards, parents, 0.8)
+    spec = synth.NetSpec(names, cards, parents, cpts)
+    _, infer = install_cpts(spec, DEV)
+    codes = synth.sample_forward_numpy(spec, 1, 0, 301)
+    for target, ev in (("b", ["e", "a"]), ("b", ["d"]), ("e", ["a"]), ("d", ["e", "a", "c"]), ("a", ["b", "c", "d", "e"])):
+        ids = [names.index(e) for e in ev]
+        _check(spec, infer, target, ev, codes[ids].T)
+
+
+def test_zero_probability_and_unseen_evidence_give_zero_rows():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.asia()
+    _, infer = install_cpts(spec, DEV)
+    # either = lung OR tub is deterministic: evidence either=0, lung=1 has probability 0
+    names = ["either", "lung", "xray"]
+    ev = np.array([[0, 1, 1], [1, 1, 0], [0, 0, 0], [255, 0, 1], [1, 255, 1], [1, 0, 255]])
+    plan = infer.plan("tub", names)
+    got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
+    want = O.ve_posterior(_net(spec), spec.names.index("tub"), [spec.names.index(e) for e in names], ev[:3])
+    np.testing.assert_allclose(got[:3], want, rtol=RTOL, atol=1e-30)
+    assert np.all(got[0] == 0) and got[1].sum() > 0.99
+    assert np.all(got[3] == 0) and np.all(got[4] == 0)
+    # xray is d-separated from tub given either: an unseen xray code is never read
+    assert got[5].sum() > 0.99
+    # zero-probability evidence in a part that is d-separated from the target still zeroes the row (oracle convention)
+    names = ["either", "lung", "tub"]
+    ev = np.array([[0, 1, 0], [1, 1, 0], [1, 0, 0]])
+    got = infer.plan("smoke", names).run_codes(_codes_matrix(ev), 3).cpu().numpy()
+    want = O.ve_posterior(_net(spec), spec.names.index("smoke"), [spec.names.index(e) for e in names], ev)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+    assert np.all(got[0] == 0) and np.all(got[2] == 0)
+
+
+def test_do_intervention_is_graph_surgery():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.asia()
+    _, infer = install_cpts(spec, DEV)
+    ev = np.array([[1, 1], [0, 1], [1, 0]])
+    got = infer.plan("smoke", ["lung", "dysp"], do=["lung"]).run_codes(_codes_matrix(ev), 3).cpu().numpy()
+    # mutilated network: lung has no parents (its CPT is irrelevant once it is clamped)
+    cut = synth.asia()
+    li = cut.names.index("lung")
+    cut.parents[li] = []
+    cut.cpts[li] = np.array([0.5, 0.5])
+    want = O.ve_posterior(_net(cut), cut.names.index("smoke"), [li, cut.names.index("dysp")], ev)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+    seen = infer.plan("smoke", ["lung", "dysp"]).run_codes(_codes_matrix(ev), 3).cpu().numpy()
+    assert np.abs(seen - got).max() > 1e-2           # observing lung is not the same as setting it
+
+
+def test_f32_and_host_entry_points_agree_with_codes():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.alarm()
+    t, infer = install_cpts(spec, DEV)
+    n = 3 * (1 << 20) + 77                           # several host chunks, ragged tail
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    rng = np.random.default_rng(5)
+    ev = np.stack([rng.integers(0, spec.cards[i], size=n) for i in ids], axis=1).astype(np.uint8)
+    m = _codes_matrix(ev)
+    plan = infer.plan("LVFAILURE", synth.ALARM_EVIDENCE)
+    a = plan.run_codes(m, n)
+    cols = [m[i, :n].to(torch.float32) for i in range(len(ids))]
+    b = plan.run_f32(cols, n)
+    assert torch.equal(a, b)
+    host_in = m.cpu()
+    out = torch.empty((n, plan.card_t), dtype=torch.float32)
+    plan.run_codes_host(host_in, n, out)
+    assert torch.equal(a.cpu(), out)
+    pin_in, pin_out = host_in.pin_memory(), torch.empty((n, plan.card_t), dtype=torch.float32).pin_memory()
+    plan.run_codes_host(pin_in, n, pin_out)
+    assert torch.equal(a.cpu(), pin_out)
+    # full-size properties: rows are distributions; identical evidence -> identical posterior
+    s = a.sum(1)
+    assert float((s - 1).abs().max()) < 1e-5
+    key = torch.zeros(n, dtype=torch.int64, device=DEV)
+    for i in range(len(ids)):
+        key = key * 4 + m[i, :n].long()
+    _, inv = torch.unique(key, return_inverse=True)
+    first = torch.full((int(inv.max()) + 1,), n, dtype=torch.int64, device=DEV).scatter_reduce(0, inv, torch.arange(n, device=DEV), "amin")
+    assert torch.equal(a, a[first[inv]])
+
+
+def test_fit_then_infer_end_to_end_on_fitted_tables():
+    """Config-2 shape end to end: sample -> count -> CPTs -> compile -> query, checked against the oracle
+    run on the oracle's own tables (counts bit-exact, so the CPTs agree to the last bit of the division)."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import fit_network_from_codes, sample_network
+
+    spec = synth.asia()
+    n = 500_000
+    codes = sample_network(spec, seed=3, first=0, n=n, device=DEV)
+    ref = synth.sample_forward_numpy(spec, 3, 0, n)
+    t, infer = fit_network_from_codes(spec, codes, n, DEV)
+    fitted = [O.cpt_from_counts(O.dense_counts(ref, spec.parents[i] + [i], spec.cards), n)[1] for i in range(spec.n)]
+    net = O.DiscreteNet(spec.cards, spec.parents, fitted)
+    ev_names = ["asia", "smoke", "xray", "dysp"]
+    ids = [spec.names.index(e) for e in ev_names]
+    ev = ref[ids][:, :4096].T
+    for target in ("lung", "tub", "bronc"):
+        got = infer.plan(target, ev_names).run_codes(_codes_matrix(ev), 4096).cpu().numpy()
+        want = O.ve_posterior(net, spec.names.index(target), ids, ev)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
