@@ -85,6 +85,9 @@ SIGNATURES = {
     "cbn_ve_plan_create_gather": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(GatherTable),
                                             C.c_int32, C.c_int32, C.POINTER(_P)]),
     "cbn_ve_plan_destroy": (None, [_P]),
+    "cbn_ve_plan_fuse": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
+    "cbn_ve_plan_outputs": (C.c_int, [_P]),
+    "cbn_ve_run_codes_multi": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P), _P]),
     "cbn_ve_run_codes": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "cbn_ve_run_f32": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.c_int64, _P, _P]),
     "cbn_ve_run_codes_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),

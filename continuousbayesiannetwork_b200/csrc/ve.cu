@@ -82,6 +82,7 @@ namespace {
 constexpr int GATHER_TPB = 256;
 constexpr int GATHER_MAX_CT = 8;           // register-resident posterior width; wider targets use the generic kernel
 constexpr int GATHER_MAX_TABLE_EV = CBN_MAX_CONTRACT_DIMS;
+constexpr int GATHER_MAX_OUT = 8;          // targets fused into one launch
 
 struct GTable {                 // device-side table descriptor (kept in shared memory by the kernel)
   const float* data;
@@ -89,8 +90,16 @@ struct GTable {                 // device-side table descriptor (kept in shared 
   int n_ev;
   int has_target;
   int smem_off;                 // >= 0: staged copy inside the CTA's shared memory (floats)
+  int out_id;                   // which posterior this table multiplies into (tables are sorted by out_id)
+  int same_index;               // 1: identical evidence slots/strides as the previous table -> reuse its index
   short slot[GATHER_MAX_TABLE_EV];
   int stride[GATHER_MAX_TABLE_EV];
+};
+static_assert(sizeof(GTable) % 8 == 0, "GTable is copied word-wise and holds a pointer");
+
+struct GatherOuts {
+  float* out[GATHER_MAX_OUT];
+  unsigned normalize_mask;
 };
 }  // namespace
 
@@ -99,10 +108,12 @@ struct cbn_ve_plan {
   int n_evidence = 0;
   int card_t = 0;
   int n_tables = 0;
-  int normalize = 1;
+  int n_out = 1;
+  unsigned normalize_mask = 1;
   std::vector<int> ev_cards;
+  std::vector<GTable> h_tables;  // host copy (smem_off = -1), used to fuse plans
   GTable* d_tables = nullptr;
-  size_t smem_bytes = 0;        // descriptors + staged tables
+  size_t smem_bytes = 0;         // descriptors + staged tables
   int staged = 0;
   long long table_bytes = 0;
 };
@@ -119,7 +130,7 @@ struct CodeLoader {
   const uint8_t* ev;
   int64_t ld;
   __device__ __forceinline__ uint32_t load4(int slot, int64_t quad) const {
-    return ld_nc_u32(reinterpret_cast<const uint32_t*>(ev + int64_t(slot) * ld) + quad);
+    return __ldg(reinterpret_cast<const uint32_t*>(ev + int64_t(slot) * ld) + quad);
   }
 };
 struct FloatLoader {
@@ -142,47 +153,27 @@ struct FloatLoader {
   }
 };
 
-template <int CT, typename Loader>
-__device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ sm_tables,
-                                             const Loader& L, int64_t quad, int64_t n_rows, int normalize,
-                                             float* __restrict__ out) {
-  float p[4][CT];
+template <int CT>
+__device__ __forceinline__ void load_slice(const float* __restrict__ src, float (&v)[CT]) {
+  if constexpr (CT == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(src);
+    v[0] = a.x; v[1] = a.y;
+  } else if constexpr (CT == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else if constexpr (CT == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int t = 0; t < CT; ++t) p[r][t] = 1.0f;
-  uint32_t bad = 0;  // one flag byte per row
-  for (int k = 0; k < n_tables; ++k) {
-    const GTable& T = st[k];
-    uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-    for (int j = 0; j < T.n_ev; ++j) {
-      const uint32_t w = L.load4(T.slot[j], quad);
-      const uint32_t s = (uint32_t)T.stride[j];
-      const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu, c3 = w >> 24;
-      bad |= (c0 == CBN_UNSEEN ? 1u : 0u) | (c1 == CBN_UNSEEN ? 0x100u : 0u) | (c2 == CBN_UNSEEN ? 0x10000u : 0u) |
-             (c3 == CBN_UNSEEN ? 0x1000000u : 0u);
-      i0 += c0 * s; i1 += c1 * s; i2 += c2 * s; i3 += c3 * s;
-    }
-    const uint32_t lim = (uint32_t)T.n_cells - (T.has_target ? CT : 1);
-    i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
-    const float* base = T.smem_off >= 0 ? sm_tables + T.smem_off : T.data;
-    const uint32_t idx[4] = {i0, i1, i2, i3};
-    if (T.has_target) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float* src = base + idx[r];
-#pragma unroll
-        for (int t = 0; t < CT; ++t) p[r][t] *= src[t];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float s = base[idx[r]];
-#pragma unroll
-        for (int t = 0; t < CT; ++t) p[r][t] *= s;
-      }
-    }
+    for (int t = 0; t < CT; ++t) v[t] = src[t];
   }
+}
+
+template <int CT>
+__device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad,
+                                             int64_t n_rows, float* __restrict__ out) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const bool rb = (bad >> (8 * r)) & 0xffu;
@@ -193,7 +184,6 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       for (int t = 0; t < CT; ++t) z += p[r][t];
       inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
     }
-    if (rb) inv = 0.0f;
 #pragma unroll
     for (int t = 0; t < CT; ++t) p[r][t] = rb ? 0.0f : p[r][t] * inv;
   }
@@ -212,6 +202,61 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
 #pragma unroll
         for (int t = 0; t < CT; ++t) dst[r * CT + t] = p[r][t];
   }
+}
+
+// One quad (4 consecutive rows): for every fused target, gather one slice per table, multiply, normalise, store.
+template <int CT, typename Loader>
+__device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ sm_tables,
+                                             const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs) {
+  float p[4][CT];
+  uint32_t bad = 0;  // one flag byte per row
+  uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, ibad = 0;
+  int cur = -1;
+  for (int k = 0; k < n_tables; ++k) {
+    const GTable& T = st[k];
+    if (T.out_id != cur) {
+      if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
+      cur = T.out_id;
+      bad = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] = 1.0f;
+    }
+    if (!T.same_index) {
+      i0 = i1 = i2 = i3 = 0; ibad = 0;
+      for (int j = 0; j < T.n_ev; ++j) {
+        const uint32_t w = L.load4(T.slot[j], quad);
+        const uint32_t s = (uint32_t)T.stride[j];
+        const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu, c3 = w >> 24;
+        ibad |= (c0 == CBN_UNSEEN ? 1u : 0u) | (c1 == CBN_UNSEEN ? 0x100u : 0u) | (c2 == CBN_UNSEEN ? 0x10000u : 0u) |
+                (c3 == CBN_UNSEEN ? 0x1000000u : 0u);
+        i0 += c0 * s; i1 += c1 * s; i2 += c2 * s; i3 += c3 * s;
+      }
+      const uint32_t lim = (uint32_t)T.n_cells - (T.has_target ? CT : 1);
+      i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
+    }
+    bad |= ibad;
+    const float* base = T.smem_off >= 0 ? sm_tables + T.smem_off : T.data;
+    const uint32_t idx[4] = {i0, i1, i2, i3};
+    if (T.has_target) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float v[CT];
+        load_slice<CT>(base + idx[r], v);
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] *= v[t];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float s = base[idx[r]];
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] *= s;
+      }
+    }
+  }
+  if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
 }
 
 // shared memory layout: [GTable x n_tables][staged tables (floats)]
@@ -237,28 +282,25 @@ __device__ __forceinline__ const float* stage_plan(const GTable* __restrict__ g_
 template <int CT>
 __global__ void __launch_bounds__(GATHER_TPB) gather_codes_kernel(const GTable* __restrict__ g_tables, int n_tables,
                                                                   const uint8_t* __restrict__ ev, int64_t ld,
-                                                                  int64_t n_rows, int normalize,
-                                                                  float* __restrict__ out) {
+                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GTable* st;
   const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
   CodeLoader L{ev, ld};
   const int64_t nquads = (n_rows + 3) >> 2;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
-    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, normalize, out);
+    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, outs);
 }
 
 template <int CT>
 __global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const GTable* __restrict__ g_tables, int n_tables,
                                                                 const __grid_constant__ EvPtrs evp, int n_evidence,
-                                                                int64_t n_rows, int normalize,
-                                                                float* __restrict__ out) {
+                                                                int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sdom_off[CBN_MAX_EVIDENCE_PTRS];
-  // domains sit at the very end of the dynamic allocation (host adds the room)
   GTable* st;
   const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
-  // locate the domain pool after descriptors + staged tables
+  // the domain pool sits after descriptors + staged tables (the host adds the room)
   int staged = 0;
   for (int k = 0; k < n_tables; ++k)
     if (st[k].smem_off >= 0) staged = max(staged, st[k].smem_off + st[k].n_cells);
@@ -274,40 +316,77 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const GTable* __
   FloatLoader L{&evp, sdom, sdom_off, n_rows};
   const int64_t nquads = (n_rows + 3) >> 2;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
-    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, normalize, out);
+    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, outs);
 }
 
 // wide targets (card_t > GATHER_MAX_CT): one thread per row, posterior accumulated in the output row
 __global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTable* __restrict__ g_tables, int n_tables,
                                                                        const uint8_t* __restrict__ ev, int64_t ld,
-                                                                       int64_t n_rows, int card_t, int normalize,
-                                                                       float* __restrict__ out) {
+                                                                       int64_t n_rows, int card_t,
+                                                                       const __grid_constant__ GatherOuts outs) {
   for (int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; row < n_rows;
        row += int64_t(gridDim.x) * blockDim.x) {
-    float* dst = out + row * card_t;
-    for (int t = 0; t < card_t; ++t) dst[t] = 1.0f;
-    bool bad = false;
-    for (int k = 0; k < n_tables; ++k) {
-      const GTable& T = g_tables[k];
-      uint32_t idx = 0;
-      for (int j = 0; j < T.n_ev; ++j) {
-        uint32_t c = ev[int64_t(T.slot[j]) * ld + row];
-        bad |= (c == CBN_UNSEEN);
-        idx += c * (uint32_t)T.stride[j];
+    int k = 0;
+    while (k < n_tables) {
+      const int cur = g_tables[k].out_id;
+      float* dst = outs.out[cur] + row * card_t;
+      for (int t = 0; t < card_t; ++t) dst[t] = 1.0f;
+      bool bad = false;
+      for (; k < n_tables && g_tables[k].out_id == cur; ++k) {
+        const GTable& T = g_tables[k];
+        uint32_t idx = 0;
+        for (int j = 0; j < T.n_ev; ++j) {
+          uint32_t c = ev[int64_t(T.slot[j]) * ld + row];
+          bad |= (c == CBN_UNSEEN);
+          idx += c * (uint32_t)T.stride[j];
+        }
+        idx = min(idx, (uint32_t)T.n_cells - (T.has_target ? card_t : 1));
+        if (T.has_target) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
+        else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] *= s; }
       }
-      idx = min(idx, (uint32_t)T.n_cells - (T.has_target ? card_t : 1));
-      if (T.has_target) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
-      else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] *= s; }
+      float inv = 1.0f;
+      if ((outs.normalize_mask >> cur) & 1u) {
+        float z = 0.0f;
+        for (int t = 0; t < card_t; ++t) z += dst[t];
+        inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
+      }
+      for (int t = 0; t < card_t; ++t) dst[t] = bad ? 0.0f : dst[t] * inv;
     }
-    float inv = 1.0f;
-    if (normalize) {
-      float z = 0.0f;
-      for (int t = 0; t < card_t; ++t) z += dst[t];
-      inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
-    }
-    if (bad) inv = 0.0f;
-    for (int t = 0; t < card_t; ++t) dst[t] = bad ? 0.0f : dst[t] * inv;
   }
+}
+
+bool same_index(const GTable& a, const GTable& b) {
+  if (a.n_ev != b.n_ev || a.has_target != b.has_target || a.n_cells != b.n_cells) return false;
+  for (int j = 0; j < a.n_ev; ++j)
+    if (a.slot[j] != b.slot[j] || a.stride[j] != b.stride[j]) return false;
+  return true;
+}
+
+// lay the tables out for the kernel (shared-memory staging, index sharing) and upload the descriptors
+int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
+  const int n = (int)p->h_tables.size();
+  long long total_cells = 0;
+  for (auto& t : p->h_tables) { total_cells += t.n_cells; t.smem_off = -1; }
+  const size_t desc_bytes = (size_t(n) * sizeof(GTable) + 15) & ~size_t(15);
+  const size_t stage_budget = 64 * 1024;   // two CTAs per SM keep their own copy
+  size_t smem = desc_bytes;
+  p->staged = 0;
+  if (size_t(total_cells) * 4 <= stage_budget) {
+    int off = 0;
+    for (auto& t : p->h_tables) { t.smem_off = off; off += (t.n_cells + 3) & ~3; }
+    smem += size_t(off) * 4;
+    p->staged = 1;
+  }
+  for (int k = 0; k < n; ++k)
+    p->h_tables[k].same_index = (k > 0 && same_index(p->h_tables[k], p->h_tables[k - 1])) ? 1 : 0;
+  p->n_tables = n;
+  p->smem_bytes = smem;
+  p->table_bytes = total_cells * 4;
+  if (p->d_tables) { cudaFree(p->d_tables); p->d_tables = nullptr; }
+  cudaError_t e = cudaMalloc((void**)&p->d_tables, sizeof(GTable) * n);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, p->h_tables.data(), sizeof(GTable) * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cbn_fail(ctx, CBN_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+  return CBN_OK;
 }
 }  // namespace
 
@@ -320,12 +399,12 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: bad argument");
   DeviceGuard g(ctx->device);
   std::vector<GTable> h(n_tables);
-  long long total_cells = 0;
   for (int k = 0; k < n_tables; ++k) {
     const cbn_gather_table& t = tables[k];
     if (!t.data || t.n_ev < 0 || t.n_ev > GATHER_MAX_TABLE_EV || t.n_cells < 1 || t.n_cells > 0x7fffffffll)
       return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: bad descriptor", k);
     long long need = t.has_target ? card_t : 1;
+    h[k] = GTable{};
     for (int j = 0; j < t.n_ev; ++j) {
       if (t.ev_slot[j] < 0 || t.ev_slot[j] >= n_evidence)
         return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: evidence slot %d out of range", k, t.ev_slot[j]);
@@ -335,35 +414,56 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
     }
     if (need > t.n_cells) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: strides address %lld cells, table has %lld", k, need, (long long)t.n_cells);
     if (t.has_target && !is_aligned(t.data, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: data must be 16-byte aligned", k);
+    if (t.has_target && card_t <= GATHER_MAX_CT)
+      for (int j = 0; j < t.n_ev; ++j)
+        if (t.ev_stride[j] % card_t != 0)
+          return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: evidence strides must be multiples of card_t (target is the fastest axis)", k);
     h[k].data = t.data; h[k].n_cells = (int)t.n_cells; h[k].n_ev = t.n_ev; h[k].has_target = t.has_target ? 1 : 0;
-    h[k].smem_off = -1;
-    total_cells += t.n_cells;
-  }
-  // stage tables in shared memory when all of them fit comfortably (two CTAs per SM keep their own copy)
-  const size_t desc_bytes = (size_t(n_tables) * sizeof(GTable) + 15) & ~size_t(15);
-  const size_t stage_budget = 64 * 1024;
-  int staged = 0;
-  size_t smem = desc_bytes;
-  if (size_t(total_cells) * 4 <= stage_budget) {
-    int off = 0;
-    for (int k = 0; k < n_tables; ++k) { h[k].smem_off = off; off += (h[k].n_cells + 3) & ~3; }
-    smem += size_t(off) * 4;
-    staged = 1;
+    h[k].smem_off = -1; h[k].out_id = 0;
   }
   cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
   if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
-  p->device = ctx->device; p->n_evidence = n_evidence; p->card_t = card_t; p->n_tables = n_tables;
-  p->normalize = normalize ? 1 : 0; p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
-  p->smem_bytes = smem; p->staged = staged; p->table_bytes = total_cells * 4;
-  cudaError_t e = cudaMalloc((void**)&p->d_tables, sizeof(GTable) * n_tables);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, h.data(), sizeof(GTable) * n_tables, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    cbn_ve_plan_destroy(p);
-    return cbn_fail(ctx, CBN_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
-  }
+  p->device = ctx->device; p->n_evidence = n_evidence; p->card_t = card_t;
+  p->n_out = 1; p->normalize_mask = normalize ? 1u : 0u;
+  p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
+  p->h_tables = h;
+  int rc = finalize_plan(ctx, p);
+  if (rc) { cbn_ve_plan_destroy(p); return rc; }
   *out = p;
   return CBN_OK;
 }
+
+extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_ve_plan** out) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_fuse: ctx is NULL");
+  if (!plans || !out || n_plans < 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: bad argument");
+  DeviceGuard g(ctx->device);
+  cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
+  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
+  p->device = ctx->device;
+  p->n_out = 0; p->normalize_mask = 0;
+  for (int i = 0; i < n_plans; ++i) {
+    const cbn_ve_plan* q = plans[i];
+    if (!q) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plan %d is NULL", i); }
+    if (i == 0) { p->n_evidence = q->n_evidence; p->ev_cards = q->ev_cards; p->card_t = q->card_t; }
+    if (q->ev_cards != p->ev_cards || q->card_t != p->card_t) {
+      delete p;
+      return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plans must share the evidence list and the target cardinality");
+    }
+    for (int o = 0; o < q->n_out; ++o) {
+      if (p->n_out >= GATHER_MAX_OUT) { delete p; return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_plan_fuse: at most %d targets per launch", GATHER_MAX_OUT); }
+      for (const GTable& t : q->h_tables)
+        if (t.out_id == o) { GTable c = t; c.out_id = p->n_out; p->h_tables.push_back(c); }
+      if ((q->normalize_mask >> o) & 1u) p->normalize_mask |= 1u << p->n_out;
+      p->n_out += 1;
+    }
+  }
+  int rc = finalize_plan(ctx, p);
+  if (rc) { cbn_ve_plan_destroy(p); return rc; }
+  *out = p;
+  return CBN_OK;
+}
+
+extern "C" int cbn_ve_plan_outputs(const cbn_ve_plan* plan) { return plan ? plan->n_out : 0; }
 
 extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
   if (!p) return;
@@ -373,69 +473,95 @@ extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
 }
 
 namespace {
+int gather_blocks(cbn_ctx* ctx, int64_t n_rows) {
+  const int64_t nquads = (n_rows + 3) >> 2;
+  return (int)std::max<int64_t>(1, std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8));
+}
 template <int CT>
-int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, float* out,
+int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
                  cudaStream_t s) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_codes_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  const int64_t nquads = (n_rows + 3) >> 2;
-  int blocks = (int)std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
-  gather_codes_kernel<CT><<<blocks, GATHER_TPB, p->smem_bytes, s>>>(p->d_tables, p->n_tables, ev, ld, n_rows, p->normalize, out);
+  gather_codes_kernel<CT><<<gather_blocks(ctx, n_rows), GATHER_TPB, p->smem_bytes, s>>>(p->d_tables, p->n_tables, ev, ld, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
 }
 template <int CT>
-int launch_f32(cbn_ctx* ctx, const cbn_ve_plan* p, const EvPtrs& evp, size_t dom_floats, int64_t n_rows, float* out,
+int launch_f32(cbn_ctx* ctx, const cbn_ve_plan* p, const EvPtrs& evp, size_t dom_floats, int64_t n_rows, const GatherOuts& outs,
                cudaStream_t s) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_f32_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  const int64_t nquads = (n_rows + 3) >> 2;
-  int blocks = (int)std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
   size_t smem = p->smem_bytes + 16 + dom_floats * 4;
-  gather_f32_kernel<CT><<<blocks, GATHER_TPB, smem, s>>>(p->d_tables, p->n_tables, evp, p->n_evidence, n_rows, p->normalize, out);
+  gather_f32_kernel<CT><<<gather_blocks(ctx, n_rows), GATHER_TPB, smem, s>>>(p->d_tables, p->n_tables, evp, p->n_evidence, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
 }
-}  // namespace
 
-static int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
-                             float* posterior, cudaStream_t s) {
+int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
+                      const GatherOuts& outs, cudaStream_t s) {
   switch (plan->card_t) {
-    case 1: return launch_codes<1>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 2: return launch_codes<2>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 3: return launch_codes<3>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 4: return launch_codes<4>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 5: return launch_codes<5>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 6: return launch_codes<6>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 7: return launch_codes<7>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
-    case 8: return launch_codes<8>(ctx, plan, ev_codes, ld, n_rows, posterior, s);
+    case 1: return launch_codes<1>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 2: return launch_codes<2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 3: return launch_codes<3>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 4: return launch_codes<4>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 5: return launch_codes<5>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 6: return launch_codes<6>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 7: return launch_codes<7>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 8: return launch_codes<8>(ctx, plan, ev_codes, ld, n_rows, outs, s);
     default: {
       int blocks = (int)std::min<int64_t>((n_rows + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
       gather_codes_wide_kernel<<<blocks, GATHER_TPB, 0, s>>>(plan->d_tables, plan->n_tables, ev_codes, ld, n_rows,
-                                                             plan->card_t, plan->normalize, posterior);
+                                                             plan->card_t, outs);
       CBN_CHECK_LAUNCH(ctx);
       return CBN_OK;
     }
   }
 }
 
+int check_run_args(cbn_ctx* ctx, const char* fn, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
+                   float* const* posteriors, GatherOuts* outs) {
+  if (!plan || !posteriors || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
+  if (plan->n_evidence > 0 && (ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "%s: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base", fn);
+  outs->normalize_mask = plan->normalize_mask;
+  for (int o = 0; o < plan->n_out; ++o) {
+    if (!posteriors[o] || !is_aligned(posteriors[o], 16))
+      return cbn_fail(ctx, CBN_ERR_INVALID, "%s: posterior %d must be a 16-byte aligned device pointer", fn, o);
+    outs->out[o] = posteriors[o];
+  }
+  return CBN_OK;
+}
+}  // namespace
+
 extern "C" int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
                                 int64_t n_rows, float* posterior, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes: ctx is NULL");
-  if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes))
-    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: bad argument");
-  if (plan->n_evidence > 0 && (ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
-    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base");
-  if (!is_aligned(posterior, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: posterior must be 16-byte aligned");
+  if (plan && plan->n_out != 1)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes: fused plan with %d outputs; use cbn_ve_run_codes_multi", plan->n_out);
+  GatherOuts outs{};
+  int rc = check_run_args(ctx, "cbn_ve_run_codes", plan, ev_codes, ld, n_rows, &posterior, &outs);
+  if (rc) return rc;
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
-  return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, posterior, (cudaStream_t)stream);
+  return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, outs, (cudaStream_t)stream);
+}
+
+extern "C" int cbn_ve_run_codes_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
+                                      int64_t n_rows, float* const* posteriors, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_multi: ctx is NULL");
+  GatherOuts outs{};
+  int rc = check_run_args(ctx, "cbn_ve_run_codes_multi", plan, ev_codes, ld, n_rows, posteriors, &outs);
+  if (rc) return rc;
+  if (n_rows == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, outs, (cudaStream_t)stream);
 }
 
 extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols,
@@ -443,6 +569,7 @@ extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_f32: ctx is NULL");
   if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && (!ev_cols || !domains)))
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: bad argument");
+  if (plan->n_out != 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: fused plans take codes (cbn_ve_run_codes_multi)");
   if (plan->n_evidence > CBN_MAX_EVIDENCE_PTRS)
     return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: more than %d evidence columns; encode them and use cbn_ve_run_codes", CBN_MAX_EVIDENCE_PTRS);
   if (plan->card_t > GATHER_MAX_CT)
@@ -457,16 +584,19 @@ extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float
     evp.col[e] = ev_cols[e]; evp.dom[e] = domains[e]; evp.card[e] = plan->ev_cards[e];
     dom_floats += plan->ev_cards[e];
   }
+  GatherOuts outs{};
+  outs.out[0] = posterior;
+  outs.normalize_mask = plan->normalize_mask;
   cudaStream_t s = (cudaStream_t)stream;
   switch (plan->card_t) {
-    case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 2: return launch_f32<2>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 3: return launch_f32<3>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 4: return launch_f32<4>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 5: return launch_f32<5>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 6: return launch_f32<6>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    case 7: return launch_f32<7>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
-    default: return launch_f32<8>(ctx, plan, evp, dom_floats, n_rows, posterior, s);
+    case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 2: return launch_f32<2>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 3: return launch_f32<3>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 4: return launch_f32<4>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 5: return launch_f32<5>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 6: return launch_f32<6>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 7: return launch_f32<7>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    default: return launch_f32<8>(ctx, plan, evp, dom_floats, n_rows, outs, s);
   }
 }
 
@@ -504,6 +634,7 @@ extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, cons
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
   if (!plan || !posterior_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
+  if (plan->n_out != 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: fused plans are device-side only");
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
   const int64_t chunk = 1 << 20;  // rows per chunk
@@ -538,7 +669,10 @@ extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, cons
     }
     if (!in_pinned && plan->n_evidence > 0)
       CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], size_t(chunk) * plan->n_evidence, cudaMemcpyHostToDevice, s));
-    rc = ve_run_codes_impl(ctx, plan, din, chunk, m, (float*)ctx->io_dev_out[b], s);
+    GatherOuts go{};
+    go.out[0] = (float*)ctx->io_dev_out[b];
+    go.normalize_mask = plan->normalize_mask;
+    rc = ve_run_codes_impl(ctx, plan, din, chunk, m, go, s);
     if (rc) return rc;
     float* dst = out_pinned ? posterior_host + r0 * plan->card_t : (float*)ctx->io_pin_out[b];
     CBN_CUDA(ctx, cudaMemcpyAsync(dst, ctx->io_dev_out[b], size_t(m) * plan->card_t * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -6,7 +6,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from ..base.inference import BaseInference
-from ..ve import QueryPlan, VECompiler
+from ..ve import FusedPlan, QueryPlan, VECompiler
 
 
 class ExactInference(BaseInference):
@@ -30,6 +30,10 @@ class ExactInference(BaseInference):
     def plan(self, target_node: str, evidence_names: Sequence[str], do: Sequence[str] = ()) -> QueryPlan:
         assert self.compiler is not None, "inference engine is not bound to a fitted network"
         return self.compiler.compile(target_node, list(evidence_names), do=do)
+
+    def fused_plan(self, targets: Sequence[str], evidence_names: Sequence[str]) -> FusedPlan:
+        """One launch for several targets that share the evidence list (same target cardinality)."""
+        return FusedPlan([self.plan(t, evidence_names) for t in targets])
 
     def _infer(self, target_node: str, evidence: Dict[str, torch.Tensor], do=None, **kwargs) -> torch.Tensor:
         """Posterior ``P(target | evidence)`` per row: float32 [n_queries, card(target)] on the device.

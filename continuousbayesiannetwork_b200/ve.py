@@ -130,6 +130,47 @@ class QueryPlan:
         return out_host
 
 
+class FusedPlan:
+    """Several targets over the same evidence list answered by ONE launch: the evidence codes are read once
+    and every target's posterior is written (``cbn_ve_plan_fuse`` / ``cbn_ve_run_codes_multi``)."""
+
+    def __init__(self, plans: Sequence[QueryPlan]):
+        assert len(plans) >= 1
+        self.plans = list(plans)            # keep the tables alive
+        self.ctx = plans[0].ctx
+        self.device = plans[0].device
+        self.card_t = plans[0].card_t
+        arr = N.ptr_array([p.handle.value for p in plans])
+        h = C.c_void_p()
+        N.check(N.lib().cbn_ve_plan_fuse(self.ctx.handle, arr, len(plans), C.byref(h)), self.ctx.handle)
+        self.handle = h
+        self.n_out = N.lib().cbn_ve_plan_outputs(h)
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                N.lib().cbn_ve_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def algorithmic_bytes_per_row(self) -> int:
+        ev = set()
+        for p in self.plans:
+            ev |= set(p.stats.relevant_evidence)
+        return len(ev) + 4 * self.card_t * self.n_out
+
+    def run_codes(self, ev_codes: torch.Tensor, n_rows: int, outs: Optional[Sequence[torch.Tensor]] = None):
+        if outs is None:
+            outs = [torch.empty((n_rows, self.card_t), dtype=torch.float32, device=self.device) for _ in range(self.n_out)]
+        assert len(outs) == self.n_out
+        ptrs = N.ptr_array([o.data_ptr() for o in outs])
+        ld = ev_codes.stride(0) if ev_codes.dim() == 2 else 0
+        N.check(N.lib().cbn_ve_run_codes_multi(self.ctx.handle, self.handle, ev_codes.data_ptr(), ld, int(n_rows), ptrs,
+                                               N.stream_ptr(self.device)), self.ctx.handle)
+        return list(outs)
+
+
 class VECompiler:
     """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
 

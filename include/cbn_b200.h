@@ -177,12 +177,20 @@ CBN_API int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const in
                               const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
                               cbn_ve_plan** out);
 CBN_API void cbn_ve_plan_destroy(cbn_ve_plan* plan);
+/* Fuse several single-target plans over the SAME evidence list and target cardinality into one plan whose
+ * launch reads the evidence once and writes every target's posterior (cbn_ve_run_codes_multi).  The fused
+ * plan references the same table memory; the inputs can be destroyed afterwards. */
+CBN_API int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_ve_plan** out);
+CBN_API int cbn_ve_plan_outputs(const cbn_ve_plan* plan);
 
 /* evidence as codes: column e of the plan's evidence list at ev_codes + e * ld.
  * posterior: device float[n_rows, card_t], rows sum to 1 (all zeros when the evidence
  * has probability 0 or contains CBN_UNSEEN). */
 CBN_API int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
                      int64_t n_rows, float* posterior, cbn_stream stream);
+/* fused plan: posteriors = host array of cbn_ve_plan_outputs(plan) device pointers */
+CBN_API int cbn_ve_run_codes_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
+                           int64_t n_rows, float* const* posteriors, cbn_stream stream);
 /* evidence as the reference hands it over: one float column per evidence variable
  * (infer's Dict[str, Tensor[nq,1]], bayesian_network.py:208-226), encoded on the fly
  * against the sorted domains.  ev_cols / domains: host arrays of device pointers. */

@@ -73,8 +73,16 @@ def test_true_posterior_where_the_reference_is_not_one(golden_dir):
                 want += p_obs[oi] * np.array([(d[sel, 2] == 0).mean(), (d[sel, 2] == 1).mean()])
         np.testing.assert_allclose(pdf[a].cpu().numpy(), want / want.sum(), rtol=2e-5)
     # evidence=None is the prior marginal (the reference raises AttributeError)
+    # (under the DAG's factorisation P(obs) P(action) P(reward | obs, action), not the raw data marginal)
     pdf, dom = bn.infer("reward", None, N_max=2)
-    np.testing.assert_allclose(pdf.cpu().numpy(), [[0.9982, 0.0018]], rtol=1e-5)
+    p_act = np.array([(d[:, 1] == a).mean() for a in range(4)])
+    want = np.zeros(2)
+    for oi, o in enumerate(g["domain_obs_0"]):
+        for a in range(4):
+            sel = (d[:, 0] == o) & (d[:, 1] == a)
+            if sel.sum():
+                want += p_obs[oi] * p_act[a] * np.array([(d[sel, 2] == 0).mean(), (d[sel, 2] == 1).mean()])
+    np.testing.assert_allclose(pdf.cpu().numpy(), [want / want.sum()], rtol=2e-5)
 
 
 def test_star_dag_with_unsorted_parents(golden_dir):

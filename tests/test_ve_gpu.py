@@ -184,6 +184,33 @@ def test_f32_and_host_entry_points_agree_with_codes():
     assert torch.equal(a, a[first[inv]])
 
 
+def test_fused_multi_target_launch_matches_single_plans():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    for spec, ev_names, targets in ((synth.asia(), ["asia", "smoke", "xray", "dysp"], ["lung", "tub", "bronc"]),
+                                    (synth.alarm(), synth.ALARM_EVIDENCE, synth.ALARM_TARGETS)):
+        _, infer = install_cpts(spec, DEV)
+        n = 100_003
+        ids = [spec.names.index(e) for e in ev_names]
+        rng = np.random.default_rng(8)
+        ev = np.stack([rng.integers(0, spec.cards[i], size=n) for i in ids], axis=1)
+        ev[7, 0] = 255                                  # an unseen code zeroes every target's row
+        m = _codes_matrix(ev)
+        fused = infer.fused_plan(targets, ev_names)
+        outs = fused.run_codes(m, n)
+        assert fused.n_out == len(targets)
+        for t, o in zip(targets, outs):
+            single = infer.plan(t, ev_names).run_codes(m, n)
+            assert torch.equal(single, o), t
+            assert bool((o[7] == 0).all())
+    # mixed target cardinalities cannot be fused
+    spec = synth.alarm()
+    _, infer = install_cpts(spec, DEV)
+    with pytest.raises(ValueError):
+        infer.fused_plan(["HYPOVOLEMIA", "VENTLUNG"], synth.ALARM_EVIDENCE)
+
+
 def test_fit_then_infer_end_to_end_on_fitted_tables():
     """Config-2 shape end to end: sample -> count -> CPTs -> compile -> query, checked against the oracle
     run on the oracle's own tables (counts bit-exact, so the CPTs agree to the last bit of the division)."""
