@@ -64,6 +64,26 @@ struct DeviceGuard {
 
 static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// validates one family descriptor; returns its table size
+static inline int check_family(cbn_ctx* ctx, const cbn_family* f, int n_cols, int64_t* n_cells_out) {
+  if (f->n_vars < 1 || f->n_vars > CBN_MAX_FAMILY_VARS)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "family has %d variables (supported: 1..%d)", f->n_vars,
+                    CBN_MAX_FAMILY_VARS);
+  int64_t cells = 1;
+  for (int j = 0; j < f->n_vars; ++j) {
+    if (n_cols >= 0 && (f->var[j] < 0 || f->var[j] >= n_cols))
+      return cbn_fail(ctx, CBN_ERR_INVALID, "family variable %d is not a column in [0,%d)", f->var[j], n_cols);
+    if (f->card[j] < 1 || f->card[j] > CBN_MAX_CARD)
+      return cbn_fail(ctx, CBN_ERR_INVALID, "cardinality %d outside [1,%d]", f->card[j], CBN_MAX_CARD);
+    cells *= f->card[j];
+    if (cells > (int64_t(1) << 31))
+      return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "family table larger than 2^31 cells");
+  }
+  *n_cells_out = cells;
+  return CBN_OK;
+}
+
+
 // ---- device helpers -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) {
   uint32_t v;

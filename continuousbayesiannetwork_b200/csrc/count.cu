@@ -1,0 +1,453 @@
+// CPT counting: one pass over the uint8 code matrix updates the count tables of EVERY family.
+// Replaces the sort-based torch.unique(dim=0, return_counts=True) of BruteForce._fit
+// (reference cbn/parameter_learning/brute_force.py:17-53) and the Python loop over nodes of
+// BayesianNetwork._train (cbn/base/bayesian_network.py:138-160).
+//
+// Kernel structure (count_tiles_kernel):
+//   * families are clustered into groups by column overlap; one CTA owns one group's tables as
+//     privatised uint32 counters in shared memory (flushed once, at the end, with 64-bit atomics);
+//   * the CTA walks tiles of 1024 samples: the group's columns of the tile are staged in shared
+//     memory by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
+//     double-buffered so the copy of tile k+1 overlaps the histogram of tile k;
+//   * every thread owns 4 consecutive samples (one 32-bit word per column) and computes the four
+//     family indices with SIMD-within-a-register arithmetic: trailing variables whose partial index
+//     fits a byte are multiplied in 4x8-bit lanes, the others in 2x16-bit lanes;
+//   * updates are shared-memory atomic increments (ATOMS.POPC.INC).
+// count_direct_kernel is the same arithmetic straight from global memory: used for the tail
+// (n % 1024 samples) and, with global atomics, for families too large for shared memory.
+#include <algorithm>
+#include <new>
+#include <set>
+
+#include "common.cuh"
+
+namespace {
+constexpr int COUNT_TPB = 256;
+constexpr int TILE = 1024;                 // samples per tile (4 per thread)
+constexpr int MAX_GCOLS = 24;              // columns staged per group
+constexpr int MAX_GROUP_CELLS = 12288;     // 48 KB of uint32 counters
+constexpr int MAX_GROUP_FAMS = 64;
+
+struct FamRec {          // direct kernel: 112 bytes, one per family
+  int32_t n_vars;
+  int32_t smem_off;      // first cell inside the group's shared-memory table
+  int32_t n_cells;
+  int32_t reserved;
+  int32_t var[CBN_MAX_FAMILY_VARS];
+  int32_t stride[CBN_MAX_FAMILY_VARS];
+};
+
+struct TileFam {         // tile kernel: 64 bytes
+  int32_t n_lo;          // variables accumulated in 4 x 8-bit lanes (partial index < 256)
+  int32_t n_hi;          // variables accumulated in 2 x 16-bit lanes
+  int32_t smem_off;
+  int32_t n_cells;
+  uint32_t var[CBN_MAX_FAMILY_VARS];   // (stride << 8) | local column; lo variables first
+};
+
+struct TileGroup {
+  int32_t fam_start, n_fams;
+  int32_t col_start, n_cols;
+  int32_t n_cells;
+  int32_t pad[3];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();   // a lost copy must not hang the GPU
+  }
+}
+
+__global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
+    const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
+    const int* __restrict__ gcols, const TileFam* __restrict__ fams, const long long* __restrict__ goff,
+    unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ int s_cols[MAX_GCOLS];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int g = blockIdx.x % n_groups;       // groups of one tile are neighbours in launch order (L2 reuse)
+  const int64_t x = blockIdx.x / n_groups;
+  const int64_t xstride = gridDim.x / n_groups;
+  const TileGroup G = groups[g];
+  TileFam* sfam = reinterpret_cast<TileFam*>(smem);
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem + size_t(G.n_fams) * sizeof(TileFam));
+  unsigned char* stage = smem + ((size_t(G.n_fams) * sizeof(TileFam) + size_t(G.n_cells) * 4 + 127) & ~size_t(127));
+  const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
+  for (int i = threadIdx.x; i < G.n_fams * int(sizeof(TileFam) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sfam)[i] = reinterpret_cast<const uint32_t*>(fams + G.fam_start)[i];
+  for (int i = threadIdx.x; i < G.n_cells; i += blockDim.x) tbl[i] = 0u;
+  if (threadIdx.x < G.n_cols) s_cols[threadIdx.x] = gcols[G.col_start + threadIdx.x];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int b) {   // warp 0 only
+    if (threadIdx.x == 0) mbar_expect_tx(&bar[b], tile_bytes);
+    __syncwarp();
+    for (int c = threadIdx.x; c < G.n_cols; c += 32)
+      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(c) * TILE, codes + int64_t(s_cols[c]) * ld + tile * TILE, TILE, &bar[b]);
+  };
+
+  int64_t t = x;
+  int buf = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
+  const uint32_t wofs = threadIdx.x * 4;
+  for (; t < n_tiles; t += xstride) {
+    const int64_t tn = t + xstride;
+    // the other buffer was released by the __syncthreads that closed the previous iteration
+    if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
+    if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+    const unsigned char* st = stage + size_t(buf) * tile_bytes + wofs;
+    for (int f = 0; f < G.n_fams; ++f) {
+      const TileFam& r = sfam[f];
+      uint32_t acc8 = 0, accE = 0, accO = 0, any = 0;
+      int j = 0;
+      for (; j < r.n_lo; ++j) {
+        const uint32_t v = r.var[j];
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
+        any |= w;
+        acc8 += w * (v >> 8);                               // 4 x 8-bit lanes, no carry between them
+      }
+      const int nv = r.n_lo + r.n_hi;
+      for (; j < nv; ++j) {
+        const uint32_t v = r.var[j];
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
+        const uint32_t s = v >> 8;
+        any |= w;
+        accE += (w & 0x00ff00ffu) * s;                      // samples 0 and 2 in 16-bit lanes
+        accO += ((w >> 8) & 0x00ff00ffu) * s;               // samples 1 and 3
+      }
+      uint32_t i0 = (acc8 & 0xffu) + (accE & 0xffffu);
+      uint32_t i1 = ((acc8 >> 8) & 0xffu) + (accO & 0xffffu);
+      uint32_t i2 = ((acc8 >> 16) & 0xffu) + (accE >> 16);
+      uint32_t i3 = (acc8 >> 24) + (accO >> 16);
+      const uint32_t nc = (uint32_t)r.n_cells;
+      if (any & 0x80808080u) {
+        // a code >= 128 (cardinality > 128, or CBN_UNSEEN): the packed lanes may have carried -- redo exactly
+        uint32_t idx[4] = {0, 0, 0, 0};
+        uint32_t badrow = 0;
+        for (int k = 0; k < nv; ++k) {
+          const uint32_t v = r.var[k];
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
+          const uint32_t s = v >> 8;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t c = (w >> (8 * q)) & 0xffu;
+            badrow |= (c == CBN_UNSEEN) ? (1u << q) : 0u;
+            idx[q] += c * s;
+          }
+        }
+        i0 = (badrow & 1u) ? nc : idx[0];
+        i1 = (badrow & 2u) ? nc : idx[1];
+        i2 = (badrow & 4u) ? nc : idx[2];
+        i3 = (badrow & 8u) ? nc : idx[3];
+      }
+      uint32_t* tb = tbl + r.smem_off;
+      if (i0 < nc) atomicAdd(tb + i0, 1u);
+      if (i1 < nc) atomicAdd(tb + i1, 1u);
+      if (i2 < nc) atomicAdd(tb + i2, 1u);
+      if (i3 < nc) atomicAdd(tb + i3, 1u);
+    }
+    __syncthreads();   // every read of this buffer is done before it is refilled
+    buf ^= 1;
+  }
+  // flush the private tables into the caller's int64 tables
+  for (int f = 0; f < G.n_fams; ++f) {
+    const TileFam& r = sfam[f];
+    unsigned long long* dst = counts + goff[G.fam_start + f];
+    const uint32_t* tb = tbl + r.smem_off;
+    for (int c = threadIdx.x; c < r.n_cells; c += blockDim.x) {
+      const uint32_t v = tb[c];
+      if (v) atomicAdd(dst + c, (unsigned long long)v);
+    }
+  }
+}
+
+// Direct-from-global variant.  GLOBAL_TABLES = false: shared-memory tables for the families [f0,f1) of
+// blockIdx.y's group; true: 64-bit global atomics (families too large for shared memory).
+template <bool GLOBAL_TABLES>
+__global__ void __launch_bounds__(COUNT_TPB) count_direct_kernel(
+    const uint8_t* __restrict__ codes, int64_t ld, int64_t n, const FamRec* __restrict__ recs,
+    const int* __restrict__ group_start, int n_recs, const long long* __restrict__ goff,
+    unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  int f0 = 0, nf = n_recs;
+  const FamRec* srec = recs;
+  uint32_t* tbl = nullptr;
+  if (!GLOBAL_TABLES) {
+    f0 = group_start[blockIdx.y];
+    nf = group_start[blockIdx.y + 1] - f0;
+    FamRec* sr = reinterpret_cast<FamRec*>(smem_u);
+    tbl = smem_u + (size_t(nf) * sizeof(FamRec)) / 4;
+    for (int i = threadIdx.x; i < nf * int(sizeof(FamRec) / 4); i += blockDim.x)
+      smem_u[i] = reinterpret_cast<const uint32_t*>(recs + f0)[i];
+    __syncthreads();
+    const int cells = sr[nf - 1].smem_off + sr[nf - 1].n_cells;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) tbl[i] = 0u;
+    __syncthreads();
+    srec = sr;
+  }
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride) {
+    for (int f = 0; f < nf; ++f) {
+      const FamRec& r = srec[f];
+      uint32_t idx = 0;
+      bool ok = true;
+      for (int j = 0; j < r.n_vars; ++j) {
+        const uint32_t c = codes[int64_t(r.var[j]) * ld + s];
+        ok &= (c != CBN_UNSEEN);
+        idx += c * (uint32_t)r.stride[j];
+      }
+      if (ok && idx < (uint32_t)r.n_cells) {
+        if (GLOBAL_TABLES) atomicAdd(counts + goff[f0 + f] + idx, 1ull);
+        else atomicAdd(tbl + r.smem_off + idx, 1u);
+      }
+    }
+  }
+  if (!GLOBAL_TABLES) {
+    __syncthreads();
+    for (int f = 0; f < nf; ++f) {
+      const FamRec& r = srec[f];
+      unsigned long long* dst = counts + goff[f0 + f];
+      const uint32_t* t = tbl + r.smem_off;
+      for (int c = threadIdx.x; c < r.n_cells; c += blockDim.x) {
+        const uint32_t v = t[c];
+        if (v) atomicAdd(dst + c, (unsigned long long)v);
+      }
+    }
+  }
+}
+}  // namespace
+
+struct cbn_count_plan {
+  int device = 0;
+  int sm_count = 148;
+  int n_fams = 0, n_cols = 0;
+  // tile kernel
+  int n_groups = 0;
+  size_t tile_smem = 0;
+  TileGroup* d_groups = nullptr;
+  int* d_gcols = nullptr;
+  TileFam* d_tfams = nullptr;
+  long long* d_tgoff = nullptr;
+  // direct kernel (tail + large families): small families grouped by the same clustering, large ones at the end
+  int n_small = 0, n_large = 0;
+  size_t direct_smem = 0;
+  std::vector<int> group_start;
+  FamRec* d_recs = nullptr;
+  int* d_group_start = nullptr;
+  long long* d_goff = nullptr;
+};
+
+extern "C" void cbn_count_plan_destroy(cbn_count_plan* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  cudaFree(p->d_groups); cudaFree(p->d_gcols); cudaFree(p->d_tfams); cudaFree(p->d_tgoff);
+  cudaFree(p->d_recs); cudaFree(p->d_group_start); cudaFree(p->d_goff);
+  delete p;
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& src) {
+  if (src.empty()) { *dst = nullptr; return cudaSuccess; }
+  cudaError_t e = cudaMalloc((void**)dst, src.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t n_fams, int32_t n_cols,
+                                     cbn_count_plan** out) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_plan_create: ctx is NULL");
+  if (!fams || n_fams < 1 || n_cols < 1 || !out)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_plan_create: bad argument");
+  DeviceGuard dg(ctx->device);
+  std::vector<int64_t> cells(n_fams);
+  std::vector<int> small, large;
+  for (int f = 0; f < n_fams; ++f) {
+    int rc = check_family(ctx, &fams[f], n_cols, &cells[f]);
+    if (rc) return rc;
+    (cells[f] <= MAX_GROUP_CELLS && fams[f].n_vars <= MAX_GCOLS ? small : large).push_back(f);
+  }
+  // ---- cluster the small families by column overlap (fewer staged columns per group = less L2 traffic)
+  std::vector<std::vector<int>> groups;
+  std::vector<std::vector<int>> group_cols;
+  {
+    std::vector<char> used(n_fams, 0);
+    size_t left = small.size();
+    size_t cursor = 0;
+    while (left > 0) {
+      while (used[small[cursor]]) ++cursor;
+      int seed = small[cursor];
+      std::vector<int> members{seed};
+      std::set<int> cols(fams[seed].var, fams[seed].var + fams[seed].n_vars);
+      int64_t gcells = cells[seed];
+      used[seed] = 1; --left;
+      while (left > 0 && (int)members.size() < MAX_GROUP_FAMS) {
+        int best = -1, best_new = 1 << 30, best_shared = -1;
+        for (int f : small) {
+          if (used[f] || gcells + cells[f] > MAX_GROUP_CELLS) continue;
+          int nnew = 0, shared = 0;
+          for (int j = 0; j < fams[f].n_vars; ++j) (cols.count(fams[f].var[j]) ? shared : nnew)++;
+          if ((int)cols.size() + nnew > MAX_GCOLS) continue;
+          if (nnew < best_new || (nnew == best_new && shared > best_shared)) { best = f; best_new = nnew; best_shared = shared; }
+        }
+        if (best < 0) break;
+        members.push_back(best);
+        for (int j = 0; j < fams[best].n_vars; ++j) cols.insert(fams[best].var[j]);
+        gcells += cells[best];
+        used[best] = 1; --left;
+      }
+      groups.push_back(members);
+      group_cols.emplace_back(cols.begin(), cols.end());
+    }
+  }
+  cbn_count_plan* p = new (std::nothrow) cbn_count_plan();
+  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
+  p->device = ctx->device; p->sm_count = ctx->sm_count; p->n_fams = n_fams; p->n_cols = n_cols;
+  p->n_groups = (int)groups.size(); p->n_small = (int)small.size(); p->n_large = (int)large.size();
+
+  std::vector<TileGroup> h_groups;
+  std::vector<int> h_gcols;
+  std::vector<TileFam> h_tfams;
+  std::vector<long long> h_goff;       // shared by both kernels: record order = group order, then large families
+  std::vector<FamRec> h_recs;
+  std::vector<int> h_group_start{0};
+  size_t tile_smem = 0, direct_smem = 0;
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    TileGroup G{};
+    G.fam_start = (int)h_tfams.size(); G.n_fams = (int)groups[gi].size();
+    G.col_start = (int)h_gcols.size(); G.n_cols = (int)group_cols[gi].size();
+    int off = 0;
+    for (int f : groups[gi]) {
+      const cbn_family& F = fams[f];
+      TileFam tf{};
+      FamRec fr{};
+      tf.smem_off = fr.smem_off = off;
+      tf.n_cells = fr.n_cells = (int)cells[f];
+      fr.n_vars = F.n_vars;
+      // strides, node fastest; walk from the node backwards: byte lanes while the partial index stays < 256
+      int64_t st = 1, reach = 0;
+      std::vector<uint32_t> lo, hi;
+      for (int j = F.n_vars - 1; j >= 0; --j) {
+        fr.var[j] = F.var[j];
+        fr.stride[j] = (int32_t)st;
+        int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), F.var[j]) - group_cols[gi].begin());
+        uint32_t packed = (uint32_t(st) << 8) | uint32_t(local);
+        reach += int64_t(F.card[j] - 1) * st;
+        if (hi.empty() && reach <= 255) lo.push_back(packed); else hi.push_back(packed);
+        st *= F.card[j];
+      }
+      tf.n_lo = (int)lo.size(); tf.n_hi = (int)hi.size();
+      int k = 0;
+      for (uint32_t v : lo) tf.var[k++] = v;
+      for (uint32_t v : hi) tf.var[k++] = v;
+      h_tfams.push_back(tf);
+      h_recs.push_back(fr);
+      h_goff.push_back(F.table_offset);
+      off += (int)cells[f];
+    }
+    G.n_cells = off;
+    for (int c : group_cols[gi]) h_gcols.push_back(c);
+    h_groups.push_back(G);
+    h_group_start.push_back((int)h_recs.size());
+    size_t s = ((size_t(G.n_fams) * sizeof(TileFam) + size_t(off) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    tile_smem = std::max(tile_smem, s);
+    direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off) * 4);
+  }
+  for (int f : large) {
+    const cbn_family& F = fams[f];
+    FamRec fr{};
+    fr.n_vars = F.n_vars; fr.n_cells = (int)cells[f];
+    int64_t st = 1;
+    for (int j = F.n_vars - 1; j >= 0; --j) { fr.var[j] = F.var[j]; fr.stride[j] = (int32_t)st; st *= F.card[j]; }
+    h_recs.push_back(fr);
+    h_goff.push_back(F.table_offset);
+  }
+  p->group_start = h_group_start;
+  p->tile_smem = tile_smem; p->direct_smem = direct_smem;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(&p->d_groups, h_groups);
+  if (e == cudaSuccess) e = upload(&p->d_gcols, h_gcols);
+  if (e == cudaSuccess) e = upload(&p->d_tfams, h_tfams);
+  if (e == cudaSuccess) e = upload(&p->d_recs, h_recs);
+  if (e == cudaSuccess) e = upload(&p->d_group_start, h_group_start);
+  if (e == cudaSuccess) e = upload(&p->d_goff, h_goff);
+  if (e == cudaSuccess && p->n_groups > 0) {
+    e = cudaFuncSetAttribute(count_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(count_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)direct_smem);
+  }
+  if (e != cudaSuccess) {
+    cbn_count_plan_destroy(p);
+    return cbn_fail(ctx, CBN_ERR_CUDA, "count plan setup: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return CBN_OK;
+}
+
+extern "C" int cbn_count_plan_groups(const cbn_count_plan* plan) { return plan ? plan->n_groups + (plan->n_large > 0) : 0; }
+
+extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
+                             unsigned long long* counts, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run: ctx is NULL");
+  if (!plan || !codes || !counts || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
+  if (ld < n || (ld % 16) != 0 || !is_aligned(codes, 16))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: code matrix needs ld >= n, ld %% 16 == 0 and a 16-byte aligned base (ld=%lld, n=%lld)",
+                    (long long)ld, (long long)n);
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t chunk = int64_t(1) << 33;  // private uint32 counters cannot overflow below this (>= 64 CTAs per group)
+  for (int64_t start = 0; start < n; start += chunk) {
+    const int64_t m = std::min(chunk, n - start);  // start is a multiple of 2^33: alignment is preserved
+    const uint8_t* base = codes + start;
+    const int64_t n_tiles = m / TILE;
+    const int64_t tail = m - n_tiles * TILE;
+    if (plan->n_groups > 0) {
+      if (n_tiles > 0) {
+        int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (2 * plan->sm_count + plan->n_groups - 1) / plan->n_groups));
+        count_tiles_kernel<<<per_group * plan->n_groups, COUNT_TPB, plan->tile_smem, s>>>(
+            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_tfams, plan->d_goff, counts);
+        CBN_CHECK_LAUNCH(ctx);
+      }
+      if (tail > 0) {
+        dim3 grid((unsigned)((tail + COUNT_TPB - 1) / COUNT_TPB), plan->n_groups);
+        count_direct_kernel<false><<<grid, COUNT_TPB, plan->direct_smem, s>>>(base + n_tiles * TILE, ld, tail, plan->d_recs,
+                                                                               plan->d_group_start, 0, plan->d_goff, counts);
+        CBN_CHECK_LAUNCH(ctx);
+      }
+    }
+    if (plan->n_large > 0) {
+      int blocks = (int)std::min<int64_t>((m + COUNT_TPB - 1) / COUNT_TPB, int64_t(plan->sm_count) * 8);
+      count_direct_kernel<true><<<blocks, COUNT_TPB, 0, s>>>(base, ld, m, plan->d_recs + plan->n_small, nullptr, plan->n_large,
+                                                             plan->d_goff + plan->n_small, counts);
+      CBN_CHECK_LAUNCH(ctx);
+    }
+  }
+  return CBN_OK;
+}

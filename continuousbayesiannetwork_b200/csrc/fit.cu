@@ -58,24 +58,6 @@ extern "C" void cbn_ctx_destroy(cbn_ctx* ctx) {
 extern "C" const char* cbn_last_error(cbn_ctx* ctx) { return ctx ? ctx->err.c_str() : cbn_tls_error.c_str(); }
 extern "C" int cbn_device_sm_count(cbn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
-static int check_family(cbn_ctx* ctx, const cbn_family* f, int n_cols, int64_t* n_cells_out) {
-  if (f->n_vars < 1 || f->n_vars > CBN_MAX_FAMILY_VARS)
-    return cbn_fail(ctx, CBN_ERR_INVALID, "family has %d variables (supported: 1..%d)", f->n_vars,
-                    CBN_MAX_FAMILY_VARS);
-  int64_t cells = 1;
-  for (int j = 0; j < f->n_vars; ++j) {
-    if (n_cols >= 0 && (f->var[j] < 0 || f->var[j] >= n_cols))
-      return cbn_fail(ctx, CBN_ERR_INVALID, "family variable %d is not a column in [0,%d)", f->var[j], n_cols);
-    if (f->card[j] < 1 || f->card[j] > CBN_MAX_CARD)
-      return cbn_fail(ctx, CBN_ERR_INVALID, "cardinality %d outside [1,%d]", f->card[j], CBN_MAX_CARD);
-    cells *= f->card[j];
-    if (cells > (int64_t(1) << 31))
-      return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "family table larger than 2^31 cells");
-  }
-  *n_cells_out = cells;
-  return CBN_OK;
-}
-
 // =========================================================================== domain discovery
 // Distinct values of a float column (<= 255 of them) with a two-level hash set: a
 // shared-memory set per CTA, merged into a global set, then sorted by one CTA.
@@ -255,285 +237,6 @@ extern "C" int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const f
   if (vec) encode_f32_kernel<true><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
   else encode_f32_kernel<false><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
   CBN_CHECK_LAUNCH(ctx);
-  return CBN_OK;
-}
-
-// =========================================================================== counting
-namespace {
-struct FamRec {          // 112 bytes, one per family, ordered by group
-  int32_t n_vars;
-  int32_t smem_off;      // first cell inside the group's shared-memory table
-  int32_t n_cells;
-  int32_t reserved;
-  int32_t var[CBN_MAX_FAMILY_VARS];
-  int32_t stride[CBN_MAX_FAMILY_VARS];
-};
-constexpr int COUNT_TPB = 256;
-constexpr int COUNT_MAX_GROUP_FAMS = 256;
-}  // namespace
-
-struct cbn_count_plan {
-  int device = 0;
-  int n_fams = 0, n_cols = 0, n_groups = 0, n_large = 0;
-  int max_group_cells = 0, max_group_fams = 0;
-  std::vector<int> group_start;   // [n_groups+1] into recs
-  FamRec* d_recs = nullptr;       // small families first (grouped), then large ones
-  int* d_group_start = nullptr;
-  long long* d_goff = nullptr;    // global table offset per rec
-  int sm_count = 148;
-  size_t smem_cap_cells = 0;
-};
-
-namespace {
-// One CTA = one family group x a strided set of sample quads.  Tables of the group live in
-// shared memory as uint32 counters; every thread owns 4 consecutive samples per step (one
-// 32-bit load per column, coalesced 128 B per warp).
-__global__ void __launch_bounds__(COUNT_TPB) count_families_kernel(
-    const uint8_t* __restrict__ codes, int64_t ld, int64_t n, const FamRec* __restrict__ recs,
-    const int* __restrict__ group_start, const long long* __restrict__ goff,
-    unsigned long long* __restrict__ counts) {
-  extern __shared__ __align__(16) uint32_t smem_u32[];
-  const int g = blockIdx.y;
-  const int f0 = group_start[g], f1 = group_start[g + 1];
-  const int nf = f1 - f0;
-  FamRec* srec = reinterpret_cast<FamRec*>(smem_u32);
-  uint32_t* tbl = smem_u32 + (size_t(nf) * sizeof(FamRec)) / 4;
-  for (int i = threadIdx.x; i < nf * int(sizeof(FamRec) / 4); i += blockDim.x)
-    smem_u32[i] = reinterpret_cast<const uint32_t*>(recs + f0)[i];
-  __syncthreads();
-  const int cells = srec[nf - 1].smem_off + srec[nf - 1].n_cells;
-  for (int i = threadIdx.x; i < cells; i += blockDim.x) tbl[i] = 0u;
-  __syncthreads();
-
-  const int64_t nquads = n >> 2;
-  const int64_t qstride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += qstride) {
-    for (int f = 0; f < nf; ++f) {
-      const FamRec& r = srec[f];
-      uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-      uint32_t ff = 0;  // != 0 iff some loaded code is CBN_UNSEEN (0xFF): classic "has zero byte" on ~w
-      const int nv = r.n_vars;
-#pragma unroll 4
-      for (int j = 0; j < nv; ++j) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(codes + int64_t(r.var[j]) * ld) + q);
-        const uint32_t st = (uint32_t)r.stride[j];
-        ff |= (~w - 0x01010101u) & w & 0x80808080u;
-        i0 += (w & 0xffu) * st;
-        i1 += ((w >> 8) & 0xffu) * st;
-        i2 += ((w >> 16) & 0xffu) * st;
-        i3 += (w >> 24) * st;
-      }
-      const uint32_t nc = (uint32_t)r.n_cells;
-      uint32_t* t = tbl + r.smem_off;
-      if (ff != 0) {
-        // rare: redo the rows exactly, skipping those that hold an unseen code
-        uint32_t badrow = 0;
-        for (int j = 0; j < nv; ++j) {
-          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(codes + int64_t(r.var[j]) * ld) + q);
-          badrow |= ((w & 0xffu) == 0xffu ? 1u : 0u) | (((w >> 8) & 0xffu) == 0xffu ? 2u : 0u) |
-                    (((w >> 16) & 0xffu) == 0xffu ? 4u : 0u) | ((w >> 24) == 0xffu ? 8u : 0u);
-        }
-        if (badrow & 1u) i0 = nc;
-        if (badrow & 2u) i1 = nc;
-        if (badrow & 4u) i2 = nc;
-        if (badrow & 8u) i3 = nc;
-      }
-      if (i0 < nc) atomicAdd(t + i0, 1u);
-      if (i1 < nc) atomicAdd(t + i1, 1u);
-      if (i2 < nc) atomicAdd(t + i2, 1u);
-      if (i3 < nc) atomicAdd(t + i3, 1u);
-    }
-  }
-  // tail samples (n % 4) : first CTA of each group, scalar
-  if (blockIdx.x == 0) {
-    for (int64_t s = (nquads << 2) + threadIdx.x; s < n; s += blockDim.x) {
-      for (int f = 0; f < nf; ++f) {
-        const FamRec& r = srec[f];
-        uint32_t idx = 0;
-        bool ok = true;
-        for (int j = 0; j < r.n_vars; ++j) {
-          const uint32_t c = codes[int64_t(r.var[j]) * ld + s];
-          ok &= (c != CBN_UNSEEN);
-          idx += c * (uint32_t)r.stride[j];
-        }
-        if (ok && idx < (uint32_t)r.n_cells) atomicAdd(tbl + r.smem_off + idx, 1u);
-      }
-    }
-  }
-  __syncthreads();
-  // flush the private tables into the caller's int64 tables
-  for (int f = 0; f < nf; ++f) {
-    const FamRec& r = srec[f];
-    unsigned long long* dst = counts + goff[f0 + f];
-    const uint32_t* t = tbl + r.smem_off;
-    for (int c = threadIdx.x; c < r.n_cells; c += blockDim.x) {
-      uint32_t v = t[c];
-      if (v) atomicAdd(dst + c, (unsigned long long)v);
-    }
-  }
-}
-
-// Families whose table does not fit in shared memory: global 64-bit atomics.
-__global__ void __launch_bounds__(COUNT_TPB) count_large_kernel(
-    const uint8_t* __restrict__ codes, int64_t ld, int64_t n, const FamRec* __restrict__ recs, int n_large,
-    const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < n; s += stride) {
-    for (int f = 0; f < n_large; ++f) {
-      const FamRec& r = recs[f];
-      uint32_t idx = 0;
-      bool ok = true;
-      for (int j = 0; j < r.n_vars; ++j) {
-        uint32_t c = codes[int64_t(r.var[j]) * ld + s];
-        ok &= (c != CBN_UNSEEN);
-        idx += c * (uint32_t)r.stride[j];
-      }
-      if (ok && idx < (uint32_t)r.n_cells) atomicAdd(counts + goff[f] + idx, 1ull);
-    }
-  }
-}
-}  // namespace
-
-extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t n_fams, int32_t n_cols,
-                                     cbn_count_plan** out) {
-  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_plan_create: ctx is NULL");
-  if (!fams || n_fams < 1 || n_cols < 1 || !out)
-    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_plan_create: bad argument");
-  DeviceGuard g(ctx->device);
-  // shared-memory budget per CTA: two CTAs per SM, leave room for L1
-  const size_t smem_budget = std::min<size_t>(ctx->smem_optin, 96 * 1024);
-  std::vector<FamRec> small, large;
-  std::vector<long long> goff_small, goff_large;
-  std::vector<int> group_start{0};
-  size_t cur_bytes = 0;
-  int cur_fams = 0;
-  int max_cells = 0, max_fams = 0, cur_cells = 0;
-  for (int f = 0; f < n_fams; ++f) {
-    int64_t cells = 0;
-    int rc = check_family(ctx, &fams[f], n_cols, &cells);
-    if (rc) return rc;
-    FamRec r{};
-    r.n_vars = fams[f].n_vars;
-    r.n_cells = (int32_t)cells;
-    int64_t st = 1;
-    for (int j = r.n_vars - 1; j >= 0; --j) {
-      r.var[j] = fams[f].var[j];
-      r.stride[j] = (int32_t)st;
-      st *= fams[f].card[j];
-    }
-    size_t need = size_t(cells) * 4 + sizeof(FamRec);
-    if (need + 64 > smem_budget) {
-      large.push_back(r);
-      goff_large.push_back(fams[f].table_offset);
-      continue;
-    }
-    if (cur_bytes + need > smem_budget || cur_fams >= COUNT_MAX_GROUP_FAMS) {
-      group_start.push_back((int)small.size());
-      max_cells = std::max(max_cells, cur_cells);
-      max_fams = std::max(max_fams, cur_fams);
-      cur_bytes = 0; cur_fams = 0; cur_cells = 0;
-    }
-    r.smem_off = cur_cells;
-    small.push_back(r);
-    goff_small.push_back(fams[f].table_offset);
-    cur_bytes += need; cur_fams += 1; cur_cells += (int)cells;
-  }
-  if (cur_fams > 0) {
-    group_start.push_back((int)small.size());
-    max_cells = std::max(max_cells, cur_cells);
-    max_fams = std::max(max_fams, cur_fams);
-  }
-  cbn_count_plan* p = new (std::nothrow) cbn_count_plan();
-  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
-  p->device = ctx->device;
-  p->n_fams = n_fams; p->n_cols = n_cols;
-  p->n_groups = (int)group_start.size() - 1;
-  p->n_large = (int)large.size();
-  p->max_group_cells = max_cells; p->max_group_fams = max_fams;
-  p->group_start = group_start;
-  p->sm_count = ctx->sm_count;
-  std::vector<FamRec> all = small;
-  all.insert(all.end(), large.begin(), large.end());
-  std::vector<long long> goff = goff_small;
-  goff.insert(goff.end(), goff_large.begin(), goff_large.end());
-  cudaError_t e;
-  if ((e = cudaMalloc((void**)&p->d_recs, all.size() * sizeof(FamRec))) != cudaSuccess ||
-      (e = cudaMalloc((void**)&p->d_group_start, group_start.size() * sizeof(int))) != cudaSuccess ||
-      (e = cudaMalloc((void**)&p->d_goff, goff.size() * sizeof(long long))) != cudaSuccess) {
-    cbn_count_plan_destroy(p);
-    return cbn_fail(ctx, CBN_ERR_CUDA, "cudaMalloc (count plan): %s", cudaGetErrorString(e));
-  }
-  cudaMemcpy(p->d_recs, all.data(), all.size() * sizeof(FamRec), cudaMemcpyHostToDevice);
-  cudaMemcpy(p->d_group_start, group_start.data(), group_start.size() * sizeof(int), cudaMemcpyHostToDevice);
-  e = cudaMemcpy(p->d_goff, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    cbn_count_plan_destroy(p);
-    return cbn_fail(ctx, CBN_ERR_CUDA, "cudaMemcpy (count plan): %s", cudaGetErrorString(e));
-  }
-  if (p->n_groups > 0) {
-    size_t smem = size_t(max_fams) * sizeof(FamRec) + size_t(max_cells) * 4;
-    // the kernel indexes with the group's own family count, but the allocation is the max
-    smem = 0;
-    for (int gi = 0; gi < p->n_groups; ++gi) {
-      int a = group_start[gi], b = group_start[gi + 1];
-      size_t s = size_t(b - a) * sizeof(FamRec) + size_t(small[b - 1].smem_off + small[b - 1].n_cells) * 4;
-      smem = std::max(smem, s);
-    }
-    p->smem_cap_cells = smem;
-    e = cudaFuncSetAttribute(count_families_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      cbn_count_plan_destroy(p);
-      return cbn_fail(ctx, CBN_ERR_CUDA, "cudaFuncSetAttribute(count): %s", cudaGetErrorString(e));
-    }
-  }
-  *out = p;
-  return CBN_OK;
-}
-
-extern "C" void cbn_count_plan_destroy(cbn_count_plan* p) {
-  if (!p) return;
-  DeviceGuard g(p->device);
-  if (p->d_recs) cudaFree(p->d_recs);
-  if (p->d_group_start) cudaFree(p->d_group_start);
-  if (p->d_goff) cudaFree(p->d_goff);
-  delete p;
-}
-
-extern "C" int cbn_count_plan_groups(const cbn_count_plan* plan) { return plan ? plan->n_groups + (plan->n_large > 0) : 0; }
-
-extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
-                             unsigned long long* counts, cbn_stream stream) {
-  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run: ctx is NULL");
-  if (!plan || !codes || !counts || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
-  if (ld < n || (ld % 16) != 0 || !is_aligned(codes, 16))
-    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: code matrix needs ld >= n, ld %% 16 == 0 and a 16-byte aligned base (ld=%lld, n=%lld)",
-                    (long long)ld, (long long)n);
-  if (n == 0) return CBN_OK;
-  DeviceGuard g(ctx->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t chunk = int64_t(1) << 33;  // uint32 private counters cannot overflow below this
-  for (int64_t start = 0; start < n; start += chunk) {
-    const int64_t m = std::min(chunk, n - start);  // start is a multiple of 2^33, alignment is preserved
-    const uint8_t* base = codes + start;
-    if (plan->n_groups > 0) {
-      int64_t quads = std::max<int64_t>(m >> 2, 1);
-      int64_t want = (quads + COUNT_TPB - 1) / COUNT_TPB;
-      int per_group = std::max(1, (2 * plan->sm_count + plan->n_groups - 1) / plan->n_groups);
-      // a few waves per group so the flush cost stays small next to the pass itself
-      int gx = (int)std::min<int64_t>(want, per_group);
-      dim3 grid(gx, plan->n_groups);
-      count_families_kernel<<<grid, COUNT_TPB, plan->smem_cap_cells, s>>>(base, ld, m, plan->d_recs, plan->d_group_start,
-                                                                          plan->d_goff, counts);
-      CBN_CHECK_LAUNCH(ctx);
-    }
-    if (plan->n_large > 0) {
-      int small_n = plan->group_start.empty() ? 0 : plan->group_start.back();
-      int blocks = (int)std::min<int64_t>((m + COUNT_TPB - 1) / COUNT_TPB, int64_t(plan->sm_count) * 8);
-      count_large_kernel<<<blocks, COUNT_TPB, 0, s>>>(base, ld, m, plan->d_recs + small_n, plan->n_large,
-                                                      plan->d_goff + small_n, counts);
-      CBN_CHECK_LAUNCH(ctx);
-    }
-  }
   return CBN_OK;
 }
 

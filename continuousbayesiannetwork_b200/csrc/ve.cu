@@ -83,19 +83,23 @@ constexpr int GATHER_TPB = 256;
 constexpr int GATHER_MAX_CT = 8;           // register-resident posterior width; wider targets use the generic kernel
 constexpr int GATHER_MAX_TABLE_EV = CBN_MAX_CONTRACT_DIMS;
 constexpr int GATHER_MAX_OUT = 8;          // targets fused into one launch
+constexpr int GATHER_STAGE_BYTES = 64 * 1024;
 
-struct GTable {                 // device-side table descriptor (kept in shared memory by the kernel)
+enum : int { GT_HAS_TARGET = 1, GT_SAME_INDEX = 2, GT_MODE_SHIFT = 2 };   // mode: 0 = 8-bit lanes, 1 = 16-bit lanes, 2 = 32-bit
+
+struct GTable {                 // device-side table descriptor; the kernel keeps a copy in shared memory
   const float* data;
   int n_cells;
   int n_ev;
-  int has_target;
-  int smem_off;                 // >= 0: staged copy inside the CTA's shared memory (floats)
+  int flags;
+  int smem_off;                 // >= 0: staged copy inside the CTA's shared memory (float offset in the pool)
   int out_id;                   // which posterior this table multiplies into (tables are sorted by out_id)
-  int same_index;               // 1: identical evidence slots/strides as the previous table -> reuse its index
-  short slot[GATHER_MAX_TABLE_EV];
+  int pad;
+  uint8_t slot[GATHER_MAX_TABLE_EV];
   int stride[GATHER_MAX_TABLE_EV];
+  int pad2[2];
 };
-static_assert(sizeof(GTable) % 8 == 0, "GTable is copied word-wise and holds a pointer");
+static_assert(sizeof(GTable) % 16 == 0, "GTable is copied with 128-bit loads");
 
 struct GatherOuts {
   float* out[GATHER_MAX_OUT];
@@ -111,9 +115,10 @@ struct cbn_ve_plan {
   int n_out = 1;
   unsigned normalize_mask = 1;
   std::vector<int> ev_cards;
-  std::vector<GTable> h_tables;  // host copy (smem_off = -1), used to fuse plans
-  GTable* d_tables = nullptr;
-  size_t smem_bytes = 0;         // descriptors + staged tables
+  std::vector<GTable> h_tables;  // host copy, used to fuse plans
+  unsigned char* d_blob = nullptr;  // [GTable x n_tables][staged table pool]: one straight copy into shared memory
+  size_t blob_bytes = 0;         // == dynamic shared memory of the kernel
+  size_t desc_bytes = 0;
   int staged = 0;
   long long table_bytes = 0;
 };
@@ -174,18 +179,23 @@ __device__ __forceinline__ void load_slice(const float* __restrict__ src, float 
 template <int CT>
 __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad,
                                              int64_t n_rows, float* __restrict__ out) {
+  if (normalize) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const bool rb = (bad >> (8 * r)) & 0xffu;
-    float inv = 1.0f;
-    if (normalize) {
+    for (int r = 0; r < 4; ++r) {
       float z = 0.0f;
 #pragma unroll
       for (int t = 0; t < CT; ++t) z += p[r][t];
-      inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
-    }
+      const float inv = z > 0.0f ? __frcp_rn(z) : 0.0f;
 #pragma unroll
-    for (int t = 0; t < CT; ++t) p[r][t] = rb ? 0.0f : p[r][t] * inv;
+      for (int t = 0; t < CT; ++t) p[r][t] *= inv;
+    }
+  }
+  if (bad) {   // rare: rows with an unseen evidence value are all zeros
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if ((bad >> r) & 1u)
+#pragma unroll
+        for (int t = 0; t < CT; ++t) p[r][t] = 0.0f;
   }
   const int64_t row0 = quad << 2;
   float* dst = out + row0 * CT;
@@ -204,16 +214,36 @@ __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bo
   }
 }
 
+// exact 32-bit index + unseen flags of one table for 4 rows (used when a code >= 128 shows up)
+template <typename Loader>
+__device__ __noinline__ uint32_t exact_index4(const GTable& T, const Loader& L, int64_t quad, uint32_t (&idx)[4]) {
+  uint32_t bad = 0;
+  idx[0] = idx[1] = idx[2] = idx[3] = 0;
+  for (int j = 0; j < T.n_ev; ++j) {
+    const uint32_t w = L.load4(T.slot[j], quad);
+    const uint32_t s = (uint32_t)T.stride[j];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t c = (w >> (8 * r)) & 0xffu;
+      bad |= (c == CBN_UNSEEN) ? (1u << r) : 0u;
+      idx[r] += c * s;
+    }
+  }
+  return bad;
+}
+
 // One quad (4 consecutive rows): for every fused target, gather one slice per table, multiply, normalise, store.
+// The four row indices are computed with SIMD-within-a-register arithmetic when the table is small enough.
 template <int CT, typename Loader>
-__device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ sm_tables,
+__device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ pool,
                                              const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs) {
   float p[4][CT];
-  uint32_t bad = 0;  // one flag byte per row
-  uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, ibad = 0;
+  uint32_t bad = 0, ibad = 0;
+  uint32_t idx[4] = {0, 0, 0, 0};
   int cur = -1;
   for (int k = 0; k < n_tables; ++k) {
     const GTable& T = st[k];
+    const int flags = T.flags;
     if (T.out_id != cur) {
       if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
       cur = T.out_id;
@@ -223,23 +253,48 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
 #pragma unroll
         for (int t = 0; t < CT; ++t) p[r][t] = 1.0f;
     }
-    if (!T.same_index) {
-      i0 = i1 = i2 = i3 = 0; ibad = 0;
-      for (int j = 0; j < T.n_ev; ++j) {
-        const uint32_t w = L.load4(T.slot[j], quad);
-        const uint32_t s = (uint32_t)T.stride[j];
-        const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu, c3 = w >> 24;
-        ibad |= (c0 == CBN_UNSEEN ? 1u : 0u) | (c1 == CBN_UNSEEN ? 0x100u : 0u) | (c2 == CBN_UNSEEN ? 0x10000u : 0u) |
-                (c3 == CBN_UNSEEN ? 0x1000000u : 0u);
-        i0 += c0 * s; i1 += c1 * s; i2 += c2 * s; i3 += c3 * s;
+    if (!(flags & GT_SAME_INDEX)) {
+      const int mode = flags >> GT_MODE_SHIFT;
+      const int ne = T.n_ev;
+      uint32_t any = 0;
+      if (mode == 0) {
+        uint32_t acc = 0;
+        for (int j = 0; j < ne; ++j) {
+          const uint32_t w = L.load4(T.slot[j], quad);
+          any |= w;
+          acc += w * (uint32_t)T.stride[j];            // 4 x 8-bit lanes
+        }
+        idx[0] = acc & 0xffu; idx[1] = (acc >> 8) & 0xffu; idx[2] = (acc >> 16) & 0xffu; idx[3] = acc >> 24;
+      } else if (mode == 1) {
+        uint32_t accE = 0, accO = 0;
+        for (int j = 0; j < ne; ++j) {
+          const uint32_t w = L.load4(T.slot[j], quad);
+          const uint32_t s = (uint32_t)T.stride[j];
+          any |= w;
+          accE += (w & 0x00ff00ffu) * s;               // rows 0, 2 in 16-bit lanes
+          accO += ((w >> 8) & 0x00ff00ffu) * s;        // rows 1, 3
+        }
+        idx[0] = accE & 0xffffu; idx[1] = accO & 0xffffu; idx[2] = accE >> 16; idx[3] = accO >> 16;
+      } else {
+        idx[0] = idx[1] = idx[2] = idx[3] = 0;
+        for (int j = 0; j < ne; ++j) {
+          const uint32_t w = L.load4(T.slot[j], quad);
+          const uint32_t s = (uint32_t)T.stride[j];
+          any |= w;
+          idx[0] += (w & 0xffu) * s; idx[1] += ((w >> 8) & 0xffu) * s; idx[2] += ((w >> 16) & 0xffu) * s; idx[3] += (w >> 24) * s;
+        }
       }
-      const uint32_t lim = (uint32_t)T.n_cells - (T.has_target ? CT : 1);
-      i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
+      ibad = 0;
+      if (any & 0x80808080u) {    // a code >= 128: cardinality > 128 or CBN_UNSEEN -- the packed lanes may have carried
+        ibad = exact_index4(T, L, quad, idx);
+        const uint32_t lim = (uint32_t)T.n_cells - ((flags & GT_HAS_TARGET) ? CT : 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) idx[r] = min(idx[r], lim);
+      }
     }
     bad |= ibad;
-    const float* base = T.smem_off >= 0 ? sm_tables + T.smem_off : T.data;
-    const uint32_t idx[4] = {i0, i1, i2, i3};
-    if (T.has_target) {
+    const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
+    if (flags & GT_HAS_TARGET) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         float v[CT];
@@ -259,52 +314,42 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
   if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
 }
 
-// shared memory layout: [GTable x n_tables][staged tables (floats)]
-__device__ __forceinline__ const float* stage_plan(const GTable* __restrict__ g_tables, int n_tables, unsigned char* smem,
-                                                   GTable** st_out) {
-  GTable* st = reinterpret_cast<GTable*>(smem);
-  for (int i = threadIdx.x; i < n_tables * int(sizeof(GTable) / 4); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(st)[i] = reinterpret_cast<const uint32_t*>(g_tables)[i];
+// one straight 128-bit copy of the plan blob (descriptors + staged tables) into shared memory
+__device__ __forceinline__ void stage_blob(const unsigned char* __restrict__ blob, int blob_bytes, unsigned char* smem) {
+  const uint4* src = reinterpret_cast<const uint4*>(blob);
+  uint4* dst = reinterpret_cast<uint4*>(smem);
+  for (int i = threadIdx.x; i < (blob_bytes >> 4); i += blockDim.x) dst[i] = __ldg(src + i);
   __syncthreads();
-  float* sm_tables = reinterpret_cast<float*>(smem + ((size_t(n_tables) * sizeof(GTable) + 15) & ~size_t(15)));
-  for (int k = 0; k < n_tables; ++k) {
-    if (st[k].smem_off >= 0) {
-      const float* src = st[k].data;
-      float* dstp = sm_tables + st[k].smem_off;
-      for (int i = threadIdx.x; i < st[k].n_cells; i += blockDim.x) dstp[i] = __ldg(src + i);
-    }
-  }
-  __syncthreads();
-  *st_out = st;
-  return sm_tables;
 }
 
+constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 8 : (ct <= 4 ? 6 : 4); }
+
 template <int CT>
-__global__ void __launch_bounds__(GATHER_TPB) gather_codes_kernel(const GTable* __restrict__ g_tables, int n_tables,
-                                                                  const uint8_t* __restrict__ ev, int64_t ld,
-                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+__global__ void __launch_bounds__(GATHER_TPB, gather_min_blocks(CT)) gather_codes_kernel(
+    const unsigned char* __restrict__ blob, int blob_bytes, int desc_bytes, int n_tables, const uint8_t* __restrict__ ev,
+    int64_t ld, int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GTable* st;
-  const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
+  stage_blob(blob, blob_bytes, smem_raw);
+  const GTable* st = reinterpret_cast<const GTable*>(smem_raw);
+  const float* pool = reinterpret_cast<const float*>(smem_raw + desc_bytes);
   CodeLoader L{ev, ld};
   const int64_t nquads = (n_rows + 3) >> 2;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
-    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, outs);
+    gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs);
 }
 
 template <int CT>
-__global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const GTable* __restrict__ g_tables, int n_tables,
+__global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
+                                                                int desc_bytes, int n_tables,
                                                                 const __grid_constant__ EvPtrs evp, int n_evidence,
                                                                 int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sdom_off[CBN_MAX_EVIDENCE_PTRS];
-  GTable* st;
-  const float* sm_tables = stage_plan(g_tables, n_tables, smem_raw, &st);
-  // the domain pool sits after descriptors + staged tables (the host adds the room)
-  int staged = 0;
-  for (int k = 0; k < n_tables; ++k)
-    if (st[k].smem_off >= 0) staged = max(staged, st[k].smem_off + st[k].n_cells);
-  float* sdom = const_cast<float*>(sm_tables) + ((staged + 3) & ~3);
+  stage_blob(blob, blob_bytes, smem_raw);
+  const GTable* st = reinterpret_cast<const GTable*>(smem_raw);
+  const float* pool = reinterpret_cast<const float*>(smem_raw + desc_bytes);
+  // the domain pool sits after the blob (the host adds the room)
+  float* sdom = reinterpret_cast<float*>(smem_raw + blob_bytes);
   if (threadIdx.x == 0) {
     int off = 0;
     for (int e = 0; e < n_evidence; ++e) { sdom_off[e] = off; off += evp.card[e]; }
@@ -316,7 +361,7 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_f32_kernel(const GTable* __
   FloatLoader L{&evp, sdom, sdom_off, n_rows};
   const int64_t nquads = (n_rows + 3) >> 2;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
-    gather_rows4<CT>(st, n_tables, sm_tables, L, q, n_rows, outs);
+    gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs);
 }
 
 // wide targets (card_t > GATHER_MAX_CT): one thread per row, posterior accumulated in the output row
@@ -334,14 +379,15 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTa
       bool bad = false;
       for (; k < n_tables && g_tables[k].out_id == cur; ++k) {
         const GTable& T = g_tables[k];
+        const bool has_t = T.flags & GT_HAS_TARGET;
         uint32_t idx = 0;
         for (int j = 0; j < T.n_ev; ++j) {
           uint32_t c = ev[int64_t(T.slot[j]) * ld + row];
           bad |= (c == CBN_UNSEEN);
           idx += c * (uint32_t)T.stride[j];
         }
-        idx = min(idx, (uint32_t)T.n_cells - (T.has_target ? card_t : 1));
-        if (T.has_target) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
+        idx = min(idx, (uint32_t)T.n_cells - (has_t ? card_t : 1));
+        if (has_t) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
         else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] *= s; }
       }
       float inv = 1.0f;
@@ -356,35 +402,45 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTa
 }
 
 bool same_index(const GTable& a, const GTable& b) {
-  if (a.n_ev != b.n_ev || a.has_target != b.has_target || a.n_cells != b.n_cells) return false;
+  if (a.n_ev != b.n_ev || ((a.flags ^ b.flags) & GT_HAS_TARGET) || a.n_cells != b.n_cells) return false;
   for (int j = 0; j < a.n_ev; ++j)
     if (a.slot[j] != b.slot[j] || a.stride[j] != b.stride[j]) return false;
   return true;
 }
 
-// lay the tables out for the kernel (shared-memory staging, index sharing) and upload the descriptors
+// lay the tables out for the kernel (shared-memory staging, index sharing, index arithmetic mode) and build the blob
 int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
   const int n = (int)p->h_tables.size();
   long long total_cells = 0;
   for (auto& t : p->h_tables) { total_cells += t.n_cells; t.smem_off = -1; }
-  const size_t desc_bytes = (size_t(n) * sizeof(GTable) + 15) & ~size_t(15);
-  const size_t stage_budget = 64 * 1024;   // two CTAs per SM keep their own copy
-  size_t smem = desc_bytes;
+  const size_t desc_bytes = size_t(n) * sizeof(GTable);
+  size_t pool_floats = 0;
   p->staged = 0;
-  if (size_t(total_cells) * 4 <= stage_budget) {
-    int off = 0;
-    for (auto& t : p->h_tables) { t.smem_off = off; off += (t.n_cells + 3) & ~3; }
-    smem += size_t(off) * 4;
+  if (p->card_t <= GATHER_MAX_CT && size_t(total_cells) * 4 + size_t(n) * 16 <= GATHER_STAGE_BYTES) {
+    for (auto& t : p->h_tables) { t.smem_off = (int)pool_floats; pool_floats += (t.n_cells + 3) & ~3; }
     p->staged = 1;
   }
-  for (int k = 0; k < n; ++k)
-    p->h_tables[k].same_index = (k > 0 && same_index(p->h_tables[k], p->h_tables[k - 1])) ? 1 : 0;
+  for (int k = 0; k < n; ++k) {
+    GTable& t = p->h_tables[k];
+    long long reach = (t.flags & GT_HAS_TARGET) ? 0 : 0;
+    for (int j = 0; j < t.n_ev; ++j) reach += (long long)(p->ev_cards[t.slot[j]] - 1) * t.stride[j];
+    const int mode = reach <= 255 ? 0 : (reach <= 65535 ? 1 : 2);
+    t.flags = (t.flags & GT_HAS_TARGET) | (mode << GT_MODE_SHIFT);
+    if (k > 0 && same_index(t, p->h_tables[k - 1])) t.flags |= GT_SAME_INDEX;
+  }
   p->n_tables = n;
-  p->smem_bytes = smem;
+  p->desc_bytes = desc_bytes;
+  p->blob_bytes = desc_bytes + pool_floats * 4;
   p->table_bytes = total_cells * 4;
-  if (p->d_tables) { cudaFree(p->d_tables); p->d_tables = nullptr; }
-  cudaError_t e = cudaMalloc((void**)&p->d_tables, sizeof(GTable) * n);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_tables, p->h_tables.data(), sizeof(GTable) * n, cudaMemcpyHostToDevice);
+  if (p->d_blob) { cudaFree(p->d_blob); p->d_blob = nullptr; }
+  cudaError_t e = cudaMalloc((void**)&p->d_blob, p->blob_bytes);
+  if (e == cudaSuccess) e = cudaMemset(p->d_blob, 0, p->blob_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, p->h_tables.data(), desc_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && p->staged)
+    for (const auto& t : p->h_tables) {
+      e = cudaMemcpy(p->d_blob + desc_bytes + size_t(t.smem_off) * 4, t.data, size_t(t.n_cells) * 4, cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) break;
+    }
   if (e != cudaSuccess) return cbn_fail(ctx, CBN_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
   return CBN_OK;
 }
@@ -394,8 +450,8 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
                                          const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
                                          cbn_ve_plan** out) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: ctx is NULL");
-  if (!out || n_evidence < 0 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD || !tables ||
-      n_tables < 1 || n_tables > CBN_MAX_GATHER_TABLES)
+  if (!out || n_evidence < 0 || n_evidence > 255 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD ||
+      !tables || n_tables < 1 || n_tables > CBN_MAX_GATHER_TABLES)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: bad argument");
   DeviceGuard g(ctx->device);
   std::vector<GTable> h(n_tables);
@@ -408,17 +464,18 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
     for (int j = 0; j < t.n_ev; ++j) {
       if (t.ev_slot[j] < 0 || t.ev_slot[j] >= n_evidence)
         return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: evidence slot %d out of range", k, t.ev_slot[j]);
+      if (t.ev_stride[j] < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: negative stride", k);
       need += (long long)(ev_cards[t.ev_slot[j]] - 1) * t.ev_stride[j];
-      h[k].slot[j] = (short)t.ev_slot[j];
+      h[k].slot[j] = (uint8_t)t.ev_slot[j];
       h[k].stride[j] = t.ev_stride[j];
     }
     if (need > t.n_cells) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: strides address %lld cells, table has %lld", k, need, (long long)t.n_cells);
-    if (t.has_target && !is_aligned(t.data, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: data must be 16-byte aligned", k);
+    if (!is_aligned(t.data, 16)) return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: data must be 16-byte aligned", k);
     if (t.has_target && card_t <= GATHER_MAX_CT)
       for (int j = 0; j < t.n_ev; ++j)
         if (t.ev_stride[j] % card_t != 0)
           return cbn_fail(ctx, CBN_ERR_INVALID, "gather table %d: evidence strides must be multiples of card_t (target is the fastest axis)", k);
-    h[k].data = t.data; h[k].n_cells = (int)t.n_cells; h[k].n_ev = t.n_ev; h[k].has_target = t.has_target ? 1 : 0;
+    h[k].data = t.data; h[k].n_cells = (int)t.n_cells; h[k].n_ev = t.n_ev; h[k].flags = t.has_target ? GT_HAS_TARGET : 0;
     h[k].smem_off = -1; h[k].out_id = 0;
   }
   cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
@@ -468,14 +525,14 @@ extern "C" int cbn_ve_plan_outputs(const cbn_ve_plan* plan) { return plan ? plan
 extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  if (p->d_tables) cudaFree(p->d_tables);
+  if (p->d_blob) cudaFree(p->d_blob);
   delete p;
 }
 
 namespace {
-int gather_blocks(cbn_ctx* ctx, int64_t n_rows) {
+int gather_blocks(cbn_ctx* ctx, int64_t n_rows, int per_sm) {
   const int64_t nquads = (n_rows + 3) >> 2;
-  return (int)std::max<int64_t>(1, std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * per_sm));
 }
 template <int CT>
 int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
@@ -485,7 +542,11 @@ int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_codes_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  gather_codes_kernel<CT><<<gather_blocks(ctx, n_rows), GATHER_TPB, p->smem_bytes, s>>>(p->d_tables, p->n_tables, ev, ld, n_rows, outs);
+  // one wave: as many CTAs as fit (register / shared-memory bound), the rest of the rows by the grid-stride loop
+  int per_sm = gather_min_blocks(CT);
+  if (p->blob_bytes > 0) per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm, (200 * 1024) / (p->blob_bytes + 1024)));
+  gather_codes_kernel<CT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
+      p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
 }
@@ -497,8 +558,10 @@ int launch_f32(cbn_ctx* ctx, const cbn_ve_plan* p, const EvPtrs& evp, size_t dom
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_f32_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  size_t smem = p->smem_bytes + 16 + dom_floats * 4;
-  gather_f32_kernel<CT><<<gather_blocks(ctx, n_rows), GATHER_TPB, smem, s>>>(p->d_tables, p->n_tables, evp, p->n_evidence, n_rows, outs);
+  size_t smem = p->blob_bytes + dom_floats * 4;
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 1024)));
+  gather_f32_kernel<CT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, smem, s>>>(
+      p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, evp, p->n_evidence, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
 }
@@ -516,8 +579,8 @@ int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_c
     case 8: return launch_codes<8>(ctx, plan, ev_codes, ld, n_rows, outs, s);
     default: {
       int blocks = (int)std::min<int64_t>((n_rows + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * 8);
-      gather_codes_wide_kernel<<<blocks, GATHER_TPB, 0, s>>>(plan->d_tables, plan->n_tables, ev_codes, ld, n_rows,
-                                                             plan->card_t, outs);
+      gather_codes_wide_kernel<<<blocks, GATHER_TPB, 0, s>>>(reinterpret_cast<const GTable*>(plan->d_blob), plan->n_tables,
+                                                             ev_codes, ld, n_rows, plan->card_t, outs);
       CBN_CHECK_LAUNCH(ctx);
       return CBN_OK;
     }
