@@ -216,20 +216,17 @@ __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bo
 
 // exact 32-bit index + unseen flags of one table for 4 rows (used when a code >= 128 shows up)
 template <typename Loader>
-__device__ __noinline__ uint32_t exact_index4(const GTable& T, const Loader& L, int64_t quad, uint32_t (&idx)[4]) {
-  uint32_t bad = 0;
-  idx[0] = idx[1] = idx[2] = idx[3] = 0;
+__device__ __noinline__ uint4 exact_index4(const GTable& T, const Loader& L, int64_t quad, uint32_t lim, uint32_t* bad_out) {
+  uint32_t bad = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   for (int j = 0; j < T.n_ev; ++j) {
     const uint32_t w = L.load4(T.slot[j], quad);
     const uint32_t s = (uint32_t)T.stride[j];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t c = (w >> (8 * r)) & 0xffu;
-      bad |= (c == CBN_UNSEEN) ? (1u << r) : 0u;
-      idx[r] += c * s;
-    }
+    const uint32_t c0 = w & 0xffu, c1 = (w >> 8) & 0xffu, c2 = (w >> 16) & 0xffu, c3 = w >> 24;
+    bad |= (c0 == CBN_UNSEEN ? 1u : 0u) | (c1 == CBN_UNSEEN ? 2u : 0u) | (c2 == CBN_UNSEEN ? 4u : 0u) | (c3 == CBN_UNSEEN ? 8u : 0u);
+    a0 += c0 * s; a1 += c1 * s; a2 += c2 * s; a3 += c3 * s;
   }
-  return bad;
+  *bad_out = bad;
+  return make_uint4(min(a0, lim), min(a1, lim), min(a2, lim), min(a3, lim));
 }
 
 // One quad (4 consecutive rows): for every fused target, gather one slice per table, multiply, normalise, store.
@@ -239,7 +236,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
                                              const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs) {
   float p[4][CT];
   uint32_t bad = 0, ibad = 0;
-  uint32_t idx[4] = {0, 0, 0, 0};
+  uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
   int cur = -1;
   for (int k = 0; k < n_tables; ++k) {
     const GTable& T = st[k];
@@ -264,7 +261,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
           any |= w;
           acc += w * (uint32_t)T.stride[j];            // 4 x 8-bit lanes
         }
-        idx[0] = acc & 0xffu; idx[1] = (acc >> 8) & 0xffu; idx[2] = (acc >> 16) & 0xffu; idx[3] = acc >> 24;
+        i0 = acc & 0xffu; i1 = (acc >> 8) & 0xffu; i2 = (acc >> 16) & 0xffu; i3 = acc >> 24;
       } else if (mode == 1) {
         uint32_t accE = 0, accO = 0;
         for (int j = 0; j < ne; ++j) {
@@ -274,26 +271,25 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
           accE += (w & 0x00ff00ffu) * s;               // rows 0, 2 in 16-bit lanes
           accO += ((w >> 8) & 0x00ff00ffu) * s;        // rows 1, 3
         }
-        idx[0] = accE & 0xffffu; idx[1] = accO & 0xffffu; idx[2] = accE >> 16; idx[3] = accO >> 16;
+        i0 = accE & 0xffffu; i1 = accO & 0xffffu; i2 = accE >> 16; i3 = accO >> 16;
       } else {
-        idx[0] = idx[1] = idx[2] = idx[3] = 0;
+        i0 = i1 = i2 = i3 = 0;
         for (int j = 0; j < ne; ++j) {
           const uint32_t w = L.load4(T.slot[j], quad);
           const uint32_t s = (uint32_t)T.stride[j];
           any |= w;
-          idx[0] += (w & 0xffu) * s; idx[1] += ((w >> 8) & 0xffu) * s; idx[2] += ((w >> 16) & 0xffu) * s; idx[3] += (w >> 24) * s;
+          i0 += (w & 0xffu) * s; i1 += ((w >> 8) & 0xffu) * s; i2 += ((w >> 16) & 0xffu) * s; i3 += (w >> 24) * s;
         }
       }
       ibad = 0;
       if (any & 0x80808080u) {    // a code >= 128: cardinality > 128 or CBN_UNSEEN -- the packed lanes may have carried
-        ibad = exact_index4(T, L, quad, idx);
-        const uint32_t lim = (uint32_t)T.n_cells - ((flags & GT_HAS_TARGET) ? CT : 1);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) idx[r] = min(idx[r], lim);
+        const uint4 e = exact_index4(T, L, quad, (uint32_t)T.n_cells - ((flags & GT_HAS_TARGET) ? CT : 1), &ibad);
+        i0 = e.x; i1 = e.y; i2 = e.z; i3 = e.w;
       }
     }
     bad |= ibad;
     const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
+    const uint32_t idx[4] = {i0, i1, i2, i3};
     if (flags & GT_HAS_TARGET) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -322,7 +318,7 @@ __device__ __forceinline__ void stage_blob(const unsigned char* __restrict__ blo
   __syncthreads();
 }
 
-constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 8 : (ct <= 4 ? 6 : 4); }
+constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 6 : (ct <= 4 ? 5 : 3); }
 
 template <int CT>
 __global__ void __launch_bounds__(GATHER_TPB, gather_min_blocks(CT)) gather_codes_kernel(
