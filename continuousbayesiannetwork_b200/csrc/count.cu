@@ -6,15 +6,17 @@
 // Kernel structure (count_tiles_kernel):
 //   * families are clustered into groups by column overlap; one CTA owns one group's tables as
 //     privatised uint32 counters in shared memory (flushed once, at the end, with 64-bit atomics);
-//   * the CTA walks tiles of 1024 samples: the group's columns of the tile are staged in shared
+//   * the CTA walks tiles of 2048 samples: the group's columns of the tile are staged in shared
 //     memory by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
 //     double-buffered so the copy of tile k+1 overlaps the histogram of tile k;
-//   * every thread owns 4 consecutive samples (one 32-bit word per column) and computes the four
-//     family indices with SIMD-within-a-register arithmetic: trailing variables whose partial index
-//     fits a byte are multiplied in 4x8-bit lanes, the others in 2x16-bit lanes;
-//   * updates are shared-memory atomic increments (ATOMS.POPC.INC).
+//   * every thread owns 8 consecutive samples (one 64-bit word per column) and walks the group's flat
+//     (variable, family) entry stream, computing the family indices with SIMD-within-a-register
+//     arithmetic: trailing variables whose partial index fits a byte are multiplied in 4x8-bit lanes,
+//     the others in 2x16-bit lanes;
+//   * updates are branch-free shared-memory atomic increments (ATOMS.POPC.INC); an out-of-range index is
+//     clamped onto a spare cell per family that is never flushed.
 // count_direct_kernel is the same arithmetic straight from global memory: used for the tail
-// (n % 1024 samples) and, with global atomics, for families too large for shared memory.
+// (n % 2048 samples) and, with global atomics, for families too large for shared memory.
 #include <algorithm>
 #include <new>
 #include <set>
@@ -23,10 +25,16 @@
 
 namespace {
 constexpr int COUNT_TPB = 256;
-constexpr int TILE = 1024;                 // samples per tile (4 per thread)
-constexpr int MAX_GCOLS = 24;              // columns staged per group
-constexpr int MAX_GROUP_CELLS = 12288;     // 48 KB of uint32 counters
+constexpr int TILE = 2048;                 // samples per tile (8 per thread: one 64-bit word per column)
+constexpr int TILE_SHIFT = 11;
+constexpr int MAX_GCOLS = 16;              // columns staged per group (2 x 16 x 2 KB of staging)
+constexpr int MAX_GROUP_CELLS = 8192;      // 32 KB of uint32 counters
 constexpr int MAX_GROUP_FAMS = 64;
+constexpr int MAX_GROUP_ENTRIES = MAX_GROUP_FAMS * 4;
+
+// flat (variable, family) entry stream of a group: bits 0-4 local column, bit 5 = 16-bit lanes, bit 6 = last
+// variable of its family, bits 8-31 stride
+enum : uint32_t { ENT_HI = 32u, ENT_LAST = 64u };
 
 struct FamRec {          // direct kernel: 112 bytes, one per family
   int32_t n_vars;
@@ -37,19 +45,12 @@ struct FamRec {          // direct kernel: 112 bytes, one per family
   int32_t stride[CBN_MAX_FAMILY_VARS];
 };
 
-struct TileFam {         // tile kernel: 64 bytes
-  int32_t n_lo;          // variables accumulated in 4 x 8-bit lanes (partial index < 256)
-  int32_t n_hi;          // variables accumulated in 2 x 16-bit lanes
-  int32_t smem_off;
-  int32_t n_cells;
-  uint32_t var[CBN_MAX_FAMILY_VARS];   // (stride << 8) | local column; lo variables first
-};
-
 struct TileGroup {
-  int32_t fam_start, n_fams;
+  int32_t fam_start, n_fams;       // into the family header / global offset arrays
   int32_t col_start, n_cols;
-  int32_t n_cells;
-  int32_t pad[3];
+  int32_t ent_start, n_entries;
+  int32_t n_cells;                 // counters of the group, one spare cell per family included
+  int32_t pad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,23 +80,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// exact redo of one family for the 8 samples of a thread (a code >= 128 was seen: cardinality > 128 or CBN_UNSEEN)
+__device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent, int e0, int e1, const unsigned char* st,
+                                                uint32_t* tb, uint32_t nc) {
+  for (int half = 0; half < 2; ++half) {
+    uint32_t idx[4] = {0, 0, 0, 0};
+    uint32_t badrow = 0;
+    for (int e = e0; e <= e1; ++e) {
+      const uint32_t v = ent[e];
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(st + ((v & 31u) << TILE_SHIFT) + 4 * half);
+      const uint32_t s = v >> 8;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t c = (w >> (8 * q)) & 0xffu;
+        badrow |= (c == CBN_UNSEEN) ? (1u << q) : 0u;
+        idx[q] += c * s;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (!((badrow >> q) & 1u) && idx[q] < nc) atomicAdd(tb + idx[q], 1u);
+  }
+}
+
 __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
-    const int* __restrict__ gcols, const TileFam* __restrict__ fams, const long long* __restrict__ goff,
-    unsigned long long* __restrict__ counts) {
+    const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ famhdr,
+    const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
+  __shared__ uint32_t s_ent[MAX_GROUP_ENTRIES];
+  __shared__ uint32_t s_hdr[MAX_GROUP_FAMS];
   __shared__ __align__(8) uint64_t bar[2];
   const int g = blockIdx.x % n_groups;       // groups of one tile are neighbours in launch order (L2 reuse)
   const int64_t x = blockIdx.x / n_groups;
   const int64_t xstride = gridDim.x / n_groups;
   const TileGroup G = groups[g];
-  TileFam* sfam = reinterpret_cast<TileFam*>(smem);
-  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem + size_t(G.n_fams) * sizeof(TileFam));
-  unsigned char* stage = smem + ((size_t(G.n_fams) * sizeof(TileFam) + size_t(G.n_cells) * 4 + 127) & ~size_t(127));
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
+  unsigned char* stage = smem + ((size_t(G.n_cells) * 4 + 127) & ~size_t(127));
   const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
-  for (int i = threadIdx.x; i < G.n_fams * int(sizeof(TileFam) / 4); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(sfam)[i] = reinterpret_cast<const uint32_t*>(fams + G.fam_start)[i];
+  for (int i = threadIdx.x; i < G.n_entries; i += blockDim.x) s_ent[i] = entries[G.ent_start + i];
+  for (int i = threadIdx.x; i < G.n_fams; i += blockDim.x) s_hdr[i] = famhdr[G.fam_start + i];
   for (int i = threadIdx.x; i < G.n_cells; i += blockDim.x) tbl[i] = 0u;
   if (threadIdx.x < G.n_cols) s_cols[threadIdx.x] = gcols[G.col_start + threadIdx.x];
   if (threadIdx.x == 0) {
@@ -108,80 +133,70 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   auto issue = [&](int64_t tile, int b) {   // warp 0 only
     if (threadIdx.x == 0) mbar_expect_tx(&bar[b], tile_bytes);
     __syncwarp();
-    for (int c = threadIdx.x; c < G.n_cols; c += 32)
-      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(c) * TILE, codes + int64_t(s_cols[c]) * ld + tile * TILE, TILE, &bar[b]);
+    if (threadIdx.x < G.n_cols)
+      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(threadIdx.x) * TILE, codes + int64_t(s_cols[threadIdx.x]) * ld + tile * TILE,
+               TILE, &bar[b]);
   };
 
   int64_t t = x;
   int buf = 0;
   uint32_t phase0 = 0, phase1 = 0;
   if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
-  const uint32_t wofs = threadIdx.x * 4;
+  const uint32_t wofs = threadIdx.x * 8;
+  const int n_entries = G.n_entries;
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
     if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
     if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
     const unsigned char* st = stage + size_t(buf) * tile_bytes + wofs;
-    for (int f = 0; f < G.n_fams; ++f) {
-      const TileFam& r = sfam[f];
-      uint32_t acc8 = 0, accE = 0, accO = 0, any = 0;
-      int j = 0;
-      for (; j < r.n_lo; ++j) {
-        const uint32_t v = r.var[j];
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
-        any |= w;
-        acc8 += w * (v >> 8);                               // 4 x 8-bit lanes, no carry between them
+    uint32_t a8x = 0, a8y = 0, aEx = 0, aOx = 0, aEy = 0, aOy = 0, any = 0;
+    int f = 0, e0 = 0;
+#pragma unroll 1
+    for (int e = 0; e < n_entries; ++e) {
+      const uint32_t v = s_ent[e];
+      const uint2 w = *reinterpret_cast<const uint2*>(st + ((v & 31u) << TILE_SHIFT));
+      const uint32_t s = v >> 8;
+      any |= w.x | w.y;
+      if (!(v & ENT_HI)) {
+        a8x += w.x * s;                                     // 4 x 8-bit lanes, no carry between them
+        a8y += w.y * s;
+      } else {
+        aEx += (w.x & 0x00ff00ffu) * s;                     // samples 0, 2 in 16-bit lanes
+        aOx += ((w.x >> 8) & 0x00ff00ffu) * s;              // samples 1, 3
+        aEy += (w.y & 0x00ff00ffu) * s;
+        aOy += ((w.y >> 8) & 0x00ff00ffu) * s;
       }
-      const int nv = r.n_lo + r.n_hi;
-      for (; j < nv; ++j) {
-        const uint32_t v = r.var[j];
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
-        const uint32_t s = v >> 8;
-        any |= w;
-        accE += (w & 0x00ff00ffu) * s;                      // samples 0 and 2 in 16-bit lanes
-        accO += ((w >> 8) & 0x00ff00ffu) * s;               // samples 1 and 3
-      }
-      uint32_t i0 = (acc8 & 0xffu) + (accE & 0xffffu);
-      uint32_t i1 = ((acc8 >> 8) & 0xffu) + (accO & 0xffffu);
-      uint32_t i2 = ((acc8 >> 16) & 0xffu) + (accE >> 16);
-      uint32_t i3 = (acc8 >> 24) + (accO >> 16);
-      const uint32_t nc = (uint32_t)r.n_cells;
-      if (any & 0x80808080u) {
-        // a code >= 128 (cardinality > 128, or CBN_UNSEEN): the packed lanes may have carried -- redo exactly
-        uint32_t idx[4] = {0, 0, 0, 0};
-        uint32_t badrow = 0;
-        for (int k = 0; k < nv; ++k) {
-          const uint32_t v = r.var[k];
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffu) * TILE);
-          const uint32_t s = v >> 8;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t c = (w >> (8 * q)) & 0xffu;
-            badrow |= (c == CBN_UNSEEN) ? (1u << q) : 0u;
-            idx[q] += c * s;
-          }
+      if (v & ENT_LAST) {
+        const uint32_t hdr = s_hdr[f++];
+        const uint32_t nc = hdr & 0xffffu;                  // cell nc is the family's spare (never flushed)
+        uint32_t* tb = tbl + (hdr >> 16);
+        if (any & 0x80808080u) {
+          count_family_exact(s_ent, e0, e, st, tb, nc);
+        } else {
+          atomicAdd(tb + min((a8x & 0xffu) + (aEx & 0xffffu), nc), 1u);
+          atomicAdd(tb + min(((a8x >> 8) & 0xffu) + (aOx & 0xffffu), nc), 1u);
+          atomicAdd(tb + min(((a8x >> 16) & 0xffu) + (aEx >> 16), nc), 1u);
+          atomicAdd(tb + min((a8x >> 24) + (aOx >> 16), nc), 1u);
+          atomicAdd(tb + min((a8y & 0xffu) + (aEy & 0xffffu), nc), 1u);
+          atomicAdd(tb + min(((a8y >> 8) & 0xffu) + (aOy & 0xffffu), nc), 1u);
+          atomicAdd(tb + min(((a8y >> 16) & 0xffu) + (aEy >> 16), nc), 1u);
+          atomicAdd(tb + min((a8y >> 24) + (aOy >> 16), nc), 1u);
         }
-        i0 = (badrow & 1u) ? nc : idx[0];
-        i1 = (badrow & 2u) ? nc : idx[1];
-        i2 = (badrow & 4u) ? nc : idx[2];
-        i3 = (badrow & 8u) ? nc : idx[3];
+        a8x = a8y = aEx = aOx = aEy = aOy = any = 0;
+        e0 = e + 1;
       }
-      uint32_t* tb = tbl + r.smem_off;
-      if (i0 < nc) atomicAdd(tb + i0, 1u);
-      if (i1 < nc) atomicAdd(tb + i1, 1u);
-      if (i2 < nc) atomicAdd(tb + i2, 1u);
-      if (i3 < nc) atomicAdd(tb + i3, 1u);
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
     buf ^= 1;
   }
   // flush the private tables into the caller's int64 tables
   for (int f = 0; f < G.n_fams; ++f) {
-    const TileFam& r = sfam[f];
+    const uint32_t hdr = s_hdr[f];
+    const int nc = int(hdr & 0xffffu);
     unsigned long long* dst = counts + goff[G.fam_start + f];
-    const uint32_t* tb = tbl + r.smem_off;
-    for (int c = threadIdx.x; c < r.n_cells; c += blockDim.x) {
+    const uint32_t* tb = tbl + (hdr >> 16);
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const uint32_t v = tb[c];
       if (v) atomicAdd(dst + c, (unsigned long long)v);
     }
@@ -253,8 +268,8 @@ struct cbn_count_plan {
   size_t tile_smem = 0;
   TileGroup* d_groups = nullptr;
   int* d_gcols = nullptr;
-  TileFam* d_tfams = nullptr;
-  long long* d_tgoff = nullptr;
+  uint32_t* d_entries = nullptr;
+  uint32_t* d_famhdr = nullptr;
   // direct kernel (tail + large families): small families grouped by the same clustering, large ones at the end
   int n_small = 0, n_large = 0;
   size_t direct_smem = 0;
@@ -267,7 +282,7 @@ struct cbn_count_plan {
 extern "C" void cbn_count_plan_destroy(cbn_count_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_groups); cudaFree(p->d_gcols); cudaFree(p->d_tfams); cudaFree(p->d_tgoff);
+  cudaFree(p->d_groups); cudaFree(p->d_gcols); cudaFree(p->d_entries); cudaFree(p->d_famhdr);
   cudaFree(p->d_recs); cudaFree(p->d_group_start); cudaFree(p->d_goff);
   delete p;
 }
@@ -305,12 +320,14 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       int seed = small[cursor];
       std::vector<int> members{seed};
       std::set<int> cols(fams[seed].var, fams[seed].var + fams[seed].n_vars);
-      int64_t gcells = cells[seed];
+      int64_t gcells = cells[seed] + 1;            // + one spare cell per family (out-of-range updates land there)
+      int gentries = fams[seed].n_vars;
       used[seed] = 1; --left;
       while (left > 0 && (int)members.size() < MAX_GROUP_FAMS) {
         int best = -1, best_new = 1 << 30, best_shared = -1;
         for (int f : small) {
-          if (used[f] || gcells + cells[f] > MAX_GROUP_CELLS) continue;
+          if (used[f] || gcells + cells[f] + 1 > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
+              gentries + fams[f].n_vars > MAX_GROUP_ENTRIES) continue;
           int nnew = 0, shared = 0;
           for (int j = 0; j < fams[f].n_vars; ++j) (cols.count(fams[f].var[j]) ? shared : nnew)++;
           if ((int)cols.size() + nnew > MAX_GCOLS) continue;
@@ -319,7 +336,8 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         if (best < 0) break;
         members.push_back(best);
         for (int j = 0; j < fams[best].n_vars; ++j) cols.insert(fams[best].var[j]);
-        gcells += cells[best];
+        gcells += cells[best] + 1;
+        gentries += fams[best].n_vars;
         used[best] = 1; --left;
       }
       groups.push_back(members);
@@ -333,51 +351,50 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
 
   std::vector<TileGroup> h_groups;
   std::vector<int> h_gcols;
-  std::vector<TileFam> h_tfams;
+  std::vector<uint32_t> h_entries, h_famhdr;
   std::vector<long long> h_goff;       // shared by both kernels: record order = group order, then large families
   std::vector<FamRec> h_recs;
   std::vector<int> h_group_start{0};
   size_t tile_smem = 0, direct_smem = 0;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     TileGroup G{};
-    G.fam_start = (int)h_tfams.size(); G.n_fams = (int)groups[gi].size();
+    G.fam_start = (int)h_famhdr.size(); G.n_fams = (int)groups[gi].size();
     G.col_start = (int)h_gcols.size(); G.n_cols = (int)group_cols[gi].size();
-    int off = 0;
+    G.ent_start = (int)h_entries.size();
+    int off = 0, off_direct = 0;
     for (int f : groups[gi]) {
       const cbn_family& F = fams[f];
-      TileFam tf{};
       FamRec fr{};
-      tf.smem_off = fr.smem_off = off;
-      tf.n_cells = fr.n_cells = (int)cells[f];
+      fr.smem_off = off_direct;
+      fr.n_cells = (int)cells[f];
       fr.n_vars = F.n_vars;
+      h_famhdr.push_back((uint32_t(off) << 16) | uint32_t(cells[f]));
       // strides, node fastest; walk from the node backwards: byte lanes while the partial index stays < 256
       int64_t st = 1, reach = 0;
-      std::vector<uint32_t> lo, hi;
+      bool hi = false;
       for (int j = F.n_vars - 1; j >= 0; --j) {
         fr.var[j] = F.var[j];
         fr.stride[j] = (int32_t)st;
-        int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), F.var[j]) - group_cols[gi].begin());
-        uint32_t packed = (uint32_t(st) << 8) | uint32_t(local);
+        const int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), F.var[j]) - group_cols[gi].begin());
         reach += int64_t(F.card[j] - 1) * st;
-        if (hi.empty() && reach <= 255) lo.push_back(packed); else hi.push_back(packed);
+        if (reach > 255) hi = true;
+        uint32_t ent = (uint32_t(st) << 8) | uint32_t(local) | (hi ? ENT_HI : 0u) | (j == 0 ? ENT_LAST : 0u);
+        h_entries.push_back(ent);
         st *= F.card[j];
       }
-      tf.n_lo = (int)lo.size(); tf.n_hi = (int)hi.size();
-      int k = 0;
-      for (uint32_t v : lo) tf.var[k++] = v;
-      for (uint32_t v : hi) tf.var[k++] = v;
-      h_tfams.push_back(tf);
       h_recs.push_back(fr);
       h_goff.push_back(F.table_offset);
-      off += (int)cells[f];
+      off += (int)cells[f] + 1;
+      off_direct += (int)cells[f];
     }
+    G.n_entries = (int)h_entries.size() - G.ent_start;
     G.n_cells = off;
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
     h_group_start.push_back((int)h_recs.size());
-    size_t s = ((size_t(G.n_fams) * sizeof(TileFam) + size_t(off) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    size_t s = ((size_t(off) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
     tile_smem = std::max(tile_smem, s);
-    direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off) * 4);
+    direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off_direct) * 4);
   }
   for (int f : large) {
     const cbn_family& F = fams[f];
@@ -393,7 +410,8 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(&p->d_groups, h_groups);
   if (e == cudaSuccess) e = upload(&p->d_gcols, h_gcols);
-  if (e == cudaSuccess) e = upload(&p->d_tfams, h_tfams);
+  if (e == cudaSuccess) e = upload(&p->d_entries, h_entries);
+  if (e == cudaSuccess) e = upload(&p->d_famhdr, h_famhdr);
   if (e == cudaSuccess) e = upload(&p->d_recs, h_recs);
   if (e == cudaSuccess) e = upload(&p->d_group_start, h_group_start);
   if (e == cudaSuccess) e = upload(&p->d_goff, h_goff);
@@ -432,7 +450,7 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
       if (n_tiles > 0) {
         int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (2 * plan->sm_count + plan->n_groups - 1) / plan->n_groups));
         count_tiles_kernel<<<per_group * plan->n_groups, COUNT_TPB, plan->tile_smem, s>>>(
-            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_tfams, plan->d_goff, counts);
+            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_goff, counts);
         CBN_CHECK_LAUNCH(ctx);
       }
       if (tail > 0) {
