@@ -110,6 +110,13 @@ __device__ __forceinline__ void st_na_f128(float4* p, float4 v) {
                : "memory");
 }
 
+// 256-bit store (sm_100: STG.E.ENL2.256): one instruction covers a full 32-byte sector
+__device__ __forceinline__ void st_f256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // exact-match search of x in a sorted domain; CBN_UNSEEN if absent (float equality, as the
 // reference keys categories: brute_force.py:228)
 __device__ __forceinline__ int domain_code(const float* __restrict__ dom, int card, float x) {

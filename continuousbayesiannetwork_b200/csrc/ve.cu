@@ -200,11 +200,17 @@ __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bo
   const int64_t row0 = quad << 2;
   float* dst = out + row0 * CT;
   if (row0 + 4 <= n_rows) {
-    // 4 rows * CT floats are contiguous and 16-byte aligned: CT 128-bit stores
+    // 4 rows * CT floats are contiguous: 256-bit stores (one full sector per instruction) when the row block is
+    // 32-byte aligned (even CT; the host checks the base pointer), else 128-bit stores
     const float* flat = &p[0][0];
+    if ((CT % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
 #pragma unroll
-    for (int v = 0; v < CT; ++v)
-      st_na_f128(reinterpret_cast<float4*>(dst) + v, make_float4(flat[4 * v], flat[4 * v + 1], flat[4 * v + 2], flat[4 * v + 3]));
+      for (int v = 0; v < CT / 2; ++v) st_f256(dst + 8 * v, flat + 8 * v);
+    } else {
+#pragma unroll
+      for (int v = 0; v < CT; ++v)
+        st_na_f128(reinterpret_cast<float4*>(dst) + v, make_float4(flat[4 * v], flat[4 * v + 1], flat[4 * v + 2], flat[4 * v + 3]));
+    }
   } else {
 #pragma unroll
     for (int r = 0; r < 4; ++r)

@@ -8,7 +8,7 @@
 constexpr int ROWS = 1 << 20;
 constexpr int RING = 9;
 
-template <int RPT_WORDS, bool SMEM_LUT>
+template <int RPT_WORDS, bool SMEM_LUT, int STORE = 0>
 __global__ void __launch_bounds__(256) k_min(const uint8_t* __restrict__ ev, int64_t ld, int64_t n_words, const float2* __restrict__ lut,
                                             float2* __restrict__ o0, float2* __restrict__ o1, float2* __restrict__ o2) {
   __shared__ float2 s[96];
@@ -41,8 +41,15 @@ __global__ void __launch_bounds__(256) k_min(const uint8_t* __restrict__ ev, int
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
         float4* dst = reinterpret_cast<float4*>(outs[t] + (q + k) * 4);
-        dst[0] = make_float4(r[t][0].x, r[t][0].y, r[t][1].x, r[t][1].y);
-        dst[1] = make_float4(r[t][2].x, r[t][2].y, r[t][3].x, r[t][3].y);
+        if (STORE == 0) {
+          dst[0] = make_float4(r[t][0].x, r[t][0].y, r[t][1].x, r[t][1].y);
+          dst[1] = make_float4(r[t][2].x, r[t][2].y, r[t][3].x, r[t][3].y);
+        } else if (STORE == 1) {   // one 256-bit store per thread
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(r[t][0].x), "f"(r[t][0].y), "f"(r[t][1].x),
+                       "f"(r[t][1].y), "f"(r[t][2].x), "f"(r[t][2].y), "f"(r[t][3].x), "f"(r[t][3].y) : "memory");
+        } else {                   // no write at all (read + compute only): lower bound of the non-store part
+          if (r[t][0].x == 123.456f) dst[0] = make_float4(0, 0, 0, 0);
+        }
       }
     }
   }
@@ -78,6 +85,11 @@ int main() {
     snprintf(nm, sizeof nm, "1 word/thread, L1 LUT, grid %d", grid);
     report(nm, time_launches([&](int i) { int r = i % RING; k_min<1, false><<<grid, 256>>>(ev[r], ld, n_words, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
   }
+  report("1 word/thread, smem LUT, 256-bit stores, grid 1024", time_launches([&](int i) { int r = i % RING; k_min<1, true, 1><<<1024, 256>>>(ev[r], ld, n_words, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
+  report("1 word/thread, L1 LUT, 256-bit stores, grid 1024", time_launches([&](int i) { int r = i % RING; k_min<1, false, 1><<<1024, 256>>>(ev[r], ld, n_words, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
+  report("1 word/thread, L1 LUT, 256-bit stores, grid 592", time_launches([&](int i) { int r = i % RING; k_min<1, false, 1><<<592, 256>>>(ev[r], ld, n_words, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
+  report("1 word/thread, smem LUT, NO stores, grid 1024", time_launches([&](int i) { int r = i % RING; k_min<1, true, 2><<<1024, 256>>>(ev[r], ld, n_words, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
+  report("empty-ish kernel (n_words=0), grid 1024", time_launches([&](int i) { int r = i % RING; k_min<1, true, 2><<<1024, 256>>>(ev[r], ld, 0, lut, o[r*3], o[r*3+1], o[r*3+2]); }, 300));
   for (int grid : {256, 148, 296}) {
     char nm[128];
     snprintf(nm, sizeof nm, "4 words/thread (128-bit loads), smem LUT, grid %d", grid);
