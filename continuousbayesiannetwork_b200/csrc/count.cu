@@ -32,9 +32,8 @@ constexpr int MAX_GROUP_CELLS = 8192;      // 32 KB of uint32 counters
 constexpr int MAX_GROUP_FAMS = 64;
 constexpr int MAX_GROUP_ENTRIES = MAX_GROUP_FAMS * 4;
 
-// flat (variable, family) entry stream of a group: bits 0-4 local column, bit 5 = 16-bit lanes, bit 6 = last
-// variable of its family, bits 8-31 stride
-enum : uint32_t { ENT_HI = 32u, ENT_LAST = 64u };
+// entry stream of a group, family by family (byte-lane variables first, then 16-bit-lane variables):
+// bits 0-15 byte offset of the column inside a staged tile, bits 16-31 stride
 
 struct FamRec {          // direct kernel: 112 bytes, one per family
   int32_t n_vars;
@@ -86,10 +85,10 @@ __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent
   for (int half = 0; half < 2; ++half) {
     uint32_t idx[4] = {0, 0, 0, 0};
     uint32_t badrow = 0;
-    for (int e = e0; e <= e1; ++e) {
+    for (int e = e0; e < e1; ++e) {
       const uint32_t v = ent[e];
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(st + ((v & 31u) << TILE_SHIFT) + 4 * half);
-      const uint32_t s = v >> 8;
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffffu) + 4 * half);
+      const uint32_t s = v >> 16;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t c = (w >> (8 * q)) & 0xffu;
@@ -103,21 +102,22 @@ __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent
   }
 }
 
+// shared memory: [counters][entry stream][family headers][stage 0][stage 1]
 __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
-    const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ famhdr,
+    const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint2* __restrict__ famhdr,
     const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
-  __shared__ uint32_t s_ent[MAX_GROUP_ENTRIES];
-  __shared__ uint32_t s_hdr[MAX_GROUP_FAMS];
   __shared__ __align__(8) uint64_t bar[2];
   const int g = blockIdx.x % n_groups;       // groups of one tile are neighbours in launch order (L2 reuse)
   const int64_t x = blockIdx.x / n_groups;
   const int64_t xstride = gridDim.x / n_groups;
   const TileGroup G = groups[g];
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
-  unsigned char* stage = smem + ((size_t(G.n_cells) * 4 + 127) & ~size_t(127));
+  uint32_t* s_ent = tbl + G.n_cells;
+  uint2* s_hdr = reinterpret_cast<uint2*>(s_ent + ((G.n_entries + 1) & ~1));
+  unsigned char* stage = smem + ((size_t(G.n_cells) * 4 + size_t((G.n_entries + 1) & ~1) * 4 + size_t(G.n_fams) * 8 + 127) & ~size_t(127));
   const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
   for (int i = threadIdx.x; i < G.n_entries; i += blockDim.x) s_ent[i] = entries[G.ent_start + i];
   for (int i = threadIdx.x; i < G.n_fams; i += blockDim.x) s_hdr[i] = famhdr[G.fam_start + i];
@@ -143,36 +143,59 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   uint32_t phase0 = 0, phase1 = 0;
   if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
   const uint32_t wofs = threadIdx.x * 8;
-  const int n_entries = G.n_entries;
+  const int n_fams = G.n_fams;
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
     if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
     if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
     const unsigned char* st = stage + size_t(buf) * tile_bytes + wofs;
-    uint32_t a8x = 0, a8y = 0, aEx = 0, aOx = 0, aEy = 0, aOy = 0, any = 0;
-    int f = 0, e0 = 0;
+    const uint32_t* ep = s_ent;
 #pragma unroll 1
-    for (int e = 0; e < n_entries; ++e) {
-      const uint32_t v = s_ent[e];
-      const uint2 w = *reinterpret_cast<const uint2*>(st + ((v & 31u) << TILE_SHIFT));
-      const uint32_t s = v >> 8;
-      any |= w.x | w.y;
-      if (!(v & ENT_HI)) {
+    for (int f = 0; f < n_fams; ++f) {
+      const uint2 hdr = s_hdr[f];                           // x: (table offset << 16) | n_cells, y: n_lo | n_hi << 8
+      const uint32_t nc = hdr.x & 0xffffu;                  // cell nc is the family's spare (never flushed)
+      uint32_t* tb = tbl + (hdr.x >> 16);
+      const int n_lo = hdr.y & 0xffu, n_hi = (hdr.y >> 8) & 0xffu;
+      const uint32_t* e0 = ep;
+      uint32_t a8x = 0, a8y = 0, any = 0;
+#pragma unroll 1
+      for (int k = 0; k < n_lo; ++k) {
+        const uint32_t v = *ep++;
+        const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
+        const uint32_t s = v >> 16;
+        any |= w.x | w.y;
         a8x += w.x * s;                                     // 4 x 8-bit lanes, no carry between them
         a8y += w.y * s;
-      } else {
-        aEx += (w.x & 0x00ff00ffu) * s;                     // samples 0, 2 in 16-bit lanes
-        aOx += ((w.x >> 8) & 0x00ff00ffu) * s;              // samples 1, 3
-        aEy += (w.y & 0x00ff00ffu) * s;
-        aOy += ((w.y >> 8) & 0x00ff00ffu) * s;
       }
-      if (v & ENT_LAST) {
-        const uint32_t hdr = s_hdr[f++];
-        const uint32_t nc = hdr & 0xffffu;                  // cell nc is the family's spare (never flushed)
-        uint32_t* tb = tbl + (hdr >> 16);
+      if (n_hi == 0) {
         if (any & 0x80808080u) {
-          count_family_exact(s_ent, e0, e, st, tb, nc);
+          count_family_exact(s_ent, int(e0 - s_ent), int(ep - s_ent), st, tb, nc);
+        } else {
+          atomicAdd(tb + min(a8x & 0xffu, nc), 1u);
+          atomicAdd(tb + min((a8x >> 8) & 0xffu, nc), 1u);
+          atomicAdd(tb + min((a8x >> 16) & 0xffu, nc), 1u);
+          atomicAdd(tb + min(a8x >> 24, nc), 1u);
+          atomicAdd(tb + min(a8y & 0xffu, nc), 1u);
+          atomicAdd(tb + min((a8y >> 8) & 0xffu, nc), 1u);
+          atomicAdd(tb + min((a8y >> 16) & 0xffu, nc), 1u);
+          atomicAdd(tb + min(a8y >> 24, nc), 1u);
+        }
+      } else {
+        uint32_t aEx = 0, aOx = 0, aEy = 0, aOy = 0;
+#pragma unroll 1
+        for (int k = 0; k < n_hi; ++k) {
+          const uint32_t v = *ep++;
+          const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
+          const uint32_t s = v >> 16;
+          any |= w.x | w.y;
+          aEx += (w.x & 0x00ff00ffu) * s;                   // samples 0, 2 in 16-bit lanes
+          aOx += ((w.x >> 8) & 0x00ff00ffu) * s;            // samples 1, 3
+          aEy += (w.y & 0x00ff00ffu) * s;
+          aOy += ((w.y >> 8) & 0x00ff00ffu) * s;
+        }
+        if (any & 0x80808080u) {
+          count_family_exact(s_ent, int(e0 - s_ent), int(ep - s_ent), st, tb, nc);
         } else {
           atomicAdd(tb + min((a8x & 0xffu) + (aEx & 0xffffu), nc), 1u);
           atomicAdd(tb + min(((a8x >> 8) & 0xffu) + (aOx & 0xffffu), nc), 1u);
@@ -183,19 +206,17 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
           atomicAdd(tb + min(((a8y >> 16) & 0xffu) + (aEy >> 16), nc), 1u);
           atomicAdd(tb + min((a8y >> 24) + (aOy >> 16), nc), 1u);
         }
-        a8x = a8y = aEx = aOx = aEy = aOy = any = 0;
-        e0 = e + 1;
       }
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
     buf ^= 1;
   }
   // flush the private tables into the caller's int64 tables
-  for (int f = 0; f < G.n_fams; ++f) {
-    const uint32_t hdr = s_hdr[f];
-    const int nc = int(hdr & 0xffffu);
+  for (int f = 0; f < n_fams; ++f) {
+    const uint32_t h = s_hdr[f].x;
+    const int nc = int(h & 0xffffu);
     unsigned long long* dst = counts + goff[G.fam_start + f];
-    const uint32_t* tb = tbl + (hdr >> 16);
+    const uint32_t* tb = tbl + (h >> 16);
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const uint32_t v = tb[c];
       if (v) atomicAdd(dst + c, (unsigned long long)v);
@@ -265,11 +286,12 @@ struct cbn_count_plan {
   int n_fams = 0, n_cols = 0;
   // tile kernel
   int n_groups = 0;
+  int ctas_per_sm = 2;
   size_t tile_smem = 0;
   TileGroup* d_groups = nullptr;
   int* d_gcols = nullptr;
   uint32_t* d_entries = nullptr;
-  uint32_t* d_famhdr = nullptr;
+  uint2* d_famhdr = nullptr;
   // direct kernel (tail + large families): small families grouped by the same clustering, large ones at the end
   int n_small = 0, n_large = 0;
   size_t direct_smem = 0;
@@ -351,7 +373,8 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
 
   std::vector<TileGroup> h_groups;
   std::vector<int> h_gcols;
-  std::vector<uint32_t> h_entries, h_famhdr;
+  std::vector<uint32_t> h_entries;
+  std::vector<uint2> h_famhdr;
   std::vector<long long> h_goff;       // shared by both kernels: record order = group order, then large families
   std::vector<FamRec> h_recs;
   std::vector<int> h_group_start{0};
@@ -368,20 +391,19 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       fr.smem_off = off_direct;
       fr.n_cells = (int)cells[f];
       fr.n_vars = F.n_vars;
-      h_famhdr.push_back((uint32_t(off) << 16) | uint32_t(cells[f]));
       // strides, node fastest; walk from the node backwards: byte lanes while the partial index stays < 256
       int64_t st = 1, reach = 0;
-      bool hi = false;
+      int n_lo = 0, n_hi = 0;
       for (int j = F.n_vars - 1; j >= 0; --j) {
         fr.var[j] = F.var[j];
         fr.stride[j] = (int32_t)st;
         const int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), F.var[j]) - group_cols[gi].begin());
         reach += int64_t(F.card[j] - 1) * st;
-        if (reach > 255) hi = true;
-        uint32_t ent = (uint32_t(st) << 8) | uint32_t(local) | (hi ? ENT_HI : 0u) | (j == 0 ? ENT_LAST : 0u);
-        h_entries.push_back(ent);
+        if (reach > 255 || n_hi > 0) ++n_hi; else ++n_lo;
+        h_entries.push_back((uint32_t(st) << 16) | uint32_t(local * TILE));
         st *= F.card[j];
       }
+      h_famhdr.push_back(make_uint2((uint32_t(off) << 16) | uint32_t(cells[f]), uint32_t(n_lo) | (uint32_t(n_hi) << 8)));
       h_recs.push_back(fr);
       h_goff.push_back(F.table_offset);
       off += (int)cells[f] + 1;
@@ -392,7 +414,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
     h_group_start.push_back((int)h_recs.size());
-    size_t s = ((size_t(off) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    size_t s = ((size_t(off) * 4 + size_t((G.n_entries + 1) & ~1) * 4 + size_t(G.n_fams) * 8 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
     tile_smem = std::max(tile_smem, s);
     direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off_direct) * 4);
   }
@@ -417,6 +439,9 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   if (e == cudaSuccess) e = upload(&p->d_goff, h_goff);
   if (e == cudaSuccess && p->n_groups > 0) {
     e = cudaFuncSetAttribute(count_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+    int occ = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_tiles_kernel, COUNT_TPB, tile_smem);
+    p->ctas_per_sm = std::max(1, occ);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(count_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)direct_smem);
   }
@@ -448,7 +473,7 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
     const int64_t tail = m - n_tiles * TILE;
     if (plan->n_groups > 0) {
       if (n_tiles > 0) {
-        int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (2 * plan->sm_count + plan->n_groups - 1) / plan->n_groups));
+        int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (plan->ctas_per_sm * plan->sm_count) / plan->n_groups));
         count_tiles_kernel<<<per_group * plan->n_groups, COUNT_TPB, plan->tile_smem, s>>>(
             base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_goff, counts);
         CBN_CHECK_LAUNCH(ctx);

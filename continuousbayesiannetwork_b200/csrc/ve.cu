@@ -116,6 +116,8 @@ struct cbn_ve_plan {
   unsigned normalize_mask = 1;
   std::vector<int> ev_cards;
   std::vector<GTable> h_tables;  // host copy, used to fuse plans
+  float* d_inter = nullptr;      // fused plans with identical indexing: targets interleaved [cfg][target][t]
+  int interleaved = 0;           // number of targets stored in d_inter (0 = not interleaved)
   unsigned char* d_blob = nullptr;  // [GTable x n_tables][staged table pool]: one straight copy into shared memory
   size_t blob_bytes = 0;         // == dynamic shared memory of the kernel
   size_t desc_bytes = 0;
@@ -170,6 +172,11 @@ __device__ __forceinline__ void load_slice(const float* __restrict__ src, float 
     const float4 a = *reinterpret_cast<const float4*>(src);
     const float4 b = *reinterpret_cast<const float4*>(src + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else if constexpr (CT == 6) {
+    const float2 a = *reinterpret_cast<const float2*>(src);
+    const float2 b = *reinterpret_cast<const float2*>(src + 2);
+    const float2 c = *reinterpret_cast<const float2*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
   } else {
 #pragma unroll
     for (int t = 0; t < CT; ++t) v[t] = src[t];
@@ -322,6 +329,74 @@ __device__ __forceinline__ void stage_blob(const unsigned char* __restrict__ blo
   uint4* dst = reinterpret_cast<uint4*>(smem);
   for (int i = threadIdx.x; i < (blob_bytes >> 4); i += blockDim.x) dst[i] = __ldg(src + i);
   __syncthreads();
+}
+
+// Fused targets whose tables are indexed identically are stored interleaved, [configuration][target][t]: one index
+// computation and ONE contiguous slice (a single 32-byte sector for 4 binary targets) per row serve every target.
+template <int CT, int NOUT, typename Loader>
+__device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float* __restrict__ base, const Loader& L,
+                                                   int64_t quad, int64_t n_rows, const GatherOuts& outs) {
+  constexpr int W = CT * NOUT;
+  uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, any = 0, bad = 0;
+  const int mode = T.flags >> GT_MODE_SHIFT;
+  const int ne = T.n_ev;
+  if (mode == 0) {
+    uint32_t acc = 0;
+    for (int j = 0; j < ne; ++j) {
+      const uint32_t w = L.load4(T.slot[j], quad);
+      any |= w;
+      acc += w * (uint32_t)T.stride[j];
+    }
+    i0 = acc & 0xffu; i1 = (acc >> 8) & 0xffu; i2 = (acc >> 16) & 0xffu; i3 = acc >> 24;
+  } else if (mode == 1) {
+    uint32_t accE = 0, accO = 0;
+    for (int j = 0; j < ne; ++j) {
+      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t s = (uint32_t)T.stride[j];
+      any |= w;
+      accE += (w & 0x00ff00ffu) * s;
+      accO += ((w >> 8) & 0x00ff00ffu) * s;
+    }
+    i0 = accE & 0xffffu; i1 = accO & 0xffffu; i2 = accE >> 16; i3 = accO >> 16;
+  } else {
+    for (int j = 0; j < ne; ++j) {
+      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t s = (uint32_t)T.stride[j];
+      any |= w;
+      i0 += (w & 0xffu) * s; i1 += ((w >> 8) & 0xffu) * s; i2 += ((w >> 16) & 0xffu) * s; i3 += (w >> 24) * s;
+    }
+  }
+  if (any & 0x80808080u) {
+    const uint4 e = exact_index4(T, L, quad, (uint32_t)T.n_cells - W, &bad);
+    i0 = e.x; i1 = e.y; i2 = e.z; i3 = e.w;
+  }
+  const uint32_t idx[4] = {i0, i1, i2, i3};
+  float v[4][W];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) load_slice<W>(base + idx[r], v[r]);
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    float p[4][CT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int t = 0; t < CT; ++t) p[r][t] = v[r][o * CT + t];
+    finish_rows4<CT>(p, bad, false, quad, n_rows, outs.out[o]);
+  }
+}
+
+template <int CT, int NOUT>
+__global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
+                                                                  int desc_bytes, const uint8_t* __restrict__ ev, int64_t ld,
+                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  stage_blob(blob, blob_bytes, smem_raw);
+  const GTable& T = *reinterpret_cast<const GTable*>(smem_raw);
+  const float* base = T.smem_off >= 0 ? reinterpret_cast<const float*>(smem_raw + desc_bytes) + T.smem_off : T.data;
+  CodeLoader L{ev, ld};
+  const int64_t nquads = (n_rows + 3) >> 2;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
+    gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs);
 }
 
 constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 6 : (ct <= 4 ? 5 : 3); }
@@ -516,6 +591,31 @@ extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, i
       p->n_out += 1;
     }
   }
+  // identical indexing + pre-normalised single tables: interleave the targets into one table
+  {
+    const int n_out = p->n_out, ct = p->card_t, w = n_out * ct;
+    bool ok = n_out >= 2 && ct >= 2 && (int)p->h_tables.size() == n_out && p->normalize_mask == 0 && ct <= GATHER_MAX_CT &&
+              (w == 4 || w == 6 || w == 8);
+    for (int k = 0; ok && k < n_out; ++k) {
+      const GTable& t = p->h_tables[k];
+      ok = (t.flags & GT_HAS_TARGET) && t.out_id == k && (k == 0 || same_index(t, p->h_tables[0])) &&
+           (long long)t.n_cells * n_out <= 0x7fffffffll;
+    }
+    if (ok) {
+      const long long n_cfg = p->h_tables[0].n_cells / ct;
+      cudaError_t e = cudaMalloc((void**)&p->d_inter, size_t(n_cfg) * w * sizeof(float));
+      for (int k = 0; e == cudaSuccess && k < n_out; ++k)
+        e = cudaMemcpy2D(p->d_inter + k * ct, size_t(w) * sizeof(float), p->h_tables[k].data, size_t(ct) * sizeof(float),
+                         size_t(ct) * sizeof(float), size_t(n_cfg), cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) { cbn_ve_plan_destroy(p); return cbn_fail(ctx, CBN_ERR_CUDA, "interleave: %s", cudaGetErrorString(e)); }
+      GTable t = p->h_tables[0];
+      t.data = p->d_inter;
+      t.n_cells = (int)(n_cfg * w);
+      for (int j = 0; j < t.n_ev; ++j) t.stride[j] *= n_out;
+      p->h_tables.assign(1, t);
+      p->interleaved = n_out;
+    }
+  }
   int rc = finalize_plan(ctx, p);
   if (rc) { cbn_ve_plan_destroy(p); return rc; }
   *out = p;
@@ -528,6 +628,7 @@ extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
   if (p->d_blob) cudaFree(p->d_blob);
+  if (p->d_inter) cudaFree(p->d_inter);
   delete p;
 }
 
@@ -568,8 +669,34 @@ int launch_f32(cbn_ctx* ctx, const cbn_ve_plan* p, const EvPtrs& evp, size_t dom
   return CBN_OK;
 }
 
+template <int CT, int NOUT>
+int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
+                 cudaStream_t s) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_inter_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[ctx->device & 63] = true;
+  }
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (p->blob_bytes + 1024)));
+  gather_inter_kernel<CT, NOUT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
+      p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, outs);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
 int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
                       const GatherOuts& outs, cudaStream_t s) {
+  if (plan->interleaved) {
+    const int key = plan->card_t * 10 + plan->interleaved;
+    switch (key) {
+      case 22: return launch_inter<2, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 23: return launch_inter<2, 3>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 24: return launch_inter<2, 4>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 32: return launch_inter<3, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 42: return launch_inter<4, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      default: return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "internal: interleaved plan %d x %d", plan->card_t, plan->interleaved);
+    }
+  }
   switch (plan->card_t) {
     case 1: return launch_codes<1>(ctx, plan, ev_codes, ld, n_rows, outs, s);
     case 2: return launch_codes<2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
