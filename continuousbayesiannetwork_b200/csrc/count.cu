@@ -102,7 +102,7 @@ __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent
   }
 }
 
-// shared memory: [counters][entry stream][family headers][stage 0][stage 1]
+// shared memory: [counters][family headers][entry stream][stage 0][stage 1]
 __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
     const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint2* __restrict__ famhdr,
@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   const int64_t xstride = gridDim.x / n_groups;
   const TileGroup G = groups[g];
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
-  uint32_t* s_ent = tbl + G.n_cells;
-  uint2* s_hdr = reinterpret_cast<uint2*>(s_ent + ((G.n_entries + 1) & ~1));
-  unsigned char* stage = smem + ((size_t(G.n_cells) * 4 + size_t((G.n_entries + 1) & ~1) * 4 + size_t(G.n_fams) * 8 + 127) & ~size_t(127));
+  const size_t hdr_off = (size_t(G.n_cells) * 4 + 7) & ~size_t(7);
+  uint2* s_hdr = reinterpret_cast<uint2*>(smem + hdr_off);
+  uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem + hdr_off + size_t(G.n_fams) * 8);
+  unsigned char* stage = smem + ((hdr_off + size_t(G.n_fams) * 8 + size_t(G.n_entries) * 4 + 127) & ~size_t(127));
   const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
   for (int i = threadIdx.x; i < G.n_entries; i += blockDim.x) s_ent[i] = entries[G.ent_start + i];
   for (int i = threadIdx.x; i < G.n_fams; i += blockDim.x) s_hdr[i] = famhdr[G.fam_start + i];
@@ -414,7 +415,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
     h_group_start.push_back((int)h_recs.size());
-    size_t s = ((size_t(off) * 4 + size_t((G.n_entries + 1) & ~1) * 4 + size_t(G.n_fams) * 8 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    size_t s = ((((size_t(off) * 4 + 7) & ~size_t(7)) + size_t(G.n_fams) * 8 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
     tile_smem = std::max(tile_smem, s);
     direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off_direct) * 4);
   }
