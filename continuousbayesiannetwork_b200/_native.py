@@ -63,6 +63,29 @@ class GatherTable(C.Structure):
     ]
 
 
+class RowInput(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("n_cells", C.c_int64),
+        ("n_ev", C.c_int32),
+        ("ev_slot", C.c_int32 * MAX_CONTRACT_DIMS),
+        ("ev_stride", C.c_int32 * MAX_CONTRACT_DIMS),
+    ]
+
+
+class RowStep(C.Structure):
+    _fields_ = [
+        ("out_size", C.c_int32),
+        ("sum_card", C.c_int32),
+        ("n_in", C.c_int32),
+        ("in_id", C.c_int32 * MAX_CONTRACT_INPUTS),
+        ("sum_stride", C.c_int32 * MAX_CONTRACT_INPUTS),
+        ("offsets", C.c_void_p),
+    ]
+
+
+ROWS_LOG_SPACE = 1
+
 # name -> (restype, argtypes); also the list the CPU test checks against the header
 _P = C.c_void_p
 SIGNATURES = {
@@ -84,6 +107,8 @@ SIGNATURES = {
     "cbn_factor_contract": (C.c_int, [_P, C.POINTER(Contract), _P]),
     "cbn_ve_plan_create_gather": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(GatherTable),
                                             C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "cbn_ve_plan_create_rows": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(RowInput), C.c_int32,
+                                          C.POINTER(RowStep), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "cbn_ve_plan_destroy": (None, [_P]),
     "cbn_ve_plan_fuse": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
     "cbn_ve_plan_outputs": (C.c_int, [_P]),

@@ -116,6 +116,11 @@ struct cbn_ve_plan {
   unsigned normalize_mask = 1;
   std::vector<int> ev_cards;
   std::vector<GTable> h_tables;  // host copy, used to fuse plans
+  // per-row elimination plans (kind == 1)
+  int kind = 0;
+  int rows_n_inputs = 0, rows_n_steps = 0, rows_temp_floats = 0, rows_flags = 0;
+  void* d_row_inputs = nullptr;
+  void* d_row_steps = nullptr;
   float* d_inter = nullptr;      // fused plans with identical indexing: targets interleaved [cfg][target][t]
   int interleaved = 0;           // number of targets stored in d_inter (0 = not interleaved)
   unsigned char* d_blob = nullptr;  // [GTable x n_tables][staged table pool]: one straight copy into shared memory
@@ -578,6 +583,7 @@ extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, i
   for (int i = 0; i < n_plans; ++i) {
     const cbn_ve_plan* q = plans[i];
     if (!q) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plan %d is NULL", i); }
+    if (q->kind != 0) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: per-row plans cannot be fused"); }
     if (i == 0) { p->n_evidence = q->n_evidence; p->ev_cards = q->ev_cards; p->card_t = q->card_t; }
     if (q->ev_cards != p->ev_cards || q->card_t != p->card_t) {
       delete p;
@@ -629,6 +635,8 @@ extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
   DeviceGuard g(p->device);
   if (p->d_blob) cudaFree(p->d_blob);
   if (p->d_inter) cudaFree(p->d_inter);
+  if (p->d_row_inputs) cudaFree(p->d_row_inputs);
+  if (p->d_row_steps) cudaFree(p->d_row_steps);
   delete p;
 }
 
@@ -732,6 +740,211 @@ int check_run_args(cbn_ctx* ctx, const char* fn, const cbn_ve_plan* plan, const 
 }
 }  // namespace
 
+// =========================================================================== per-row elimination executor
+namespace {
+constexpr int ROWS_TPB = 256;
+constexpr int ROWS_WARPS = ROWS_TPB / 32;
+constexpr int ROWS_MAX_INPUTS = 64;
+constexpr int ROWS_MAX_STEPS = 64;
+
+struct RowInputDev {
+  const float* data;
+  int n_cells;
+  int n_ev;
+  uint8_t slot[GATHER_MAX_TABLE_EV];
+  int stride[GATHER_MAX_TABLE_EV];
+};
+struct RowStepDev {
+  const int* offsets;
+  int out_size, sum_card, n_in, temp_off;
+  int in_id[CBN_MAX_CONTRACT_INPUTS];
+  int sum_stride[CBN_MAX_CONTRACT_INPUTS];
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  Shared memory: [step descriptors][per warp: base offsets of the static inputs | temporaries].
+// Linear mode rescales every temporary by its maximum (a per-row constant cancels in the final normalisation), so
+// products of hundreds of CPT entries neither underflow nor need log space; LOG mode keeps logs and uses log-sum-exp.
+template <bool LOG>
+__global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
+                                                           const RowStepDev* __restrict__ steps, int n_steps, int temp_floats,
+                                                           const uint8_t* __restrict__ ev, int64_t ld, int64_t n_rows,
+                                                           int card_t, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowStepDev* sst = reinterpret_cast<RowStepDev*>(smem_raw);
+  for (int i = threadIdx.x; i < n_steps * int(sizeof(RowStepDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sst)[i] = reinterpret_cast<const uint32_t*>(steps)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_warp = ((n_inputs + 3) & ~3) + temp_floats;
+  int* base = reinterpret_cast<int*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev)) + size_t(warp) * per_warp;
+  float* temps = reinterpret_cast<float*>(base + ((n_inputs + 3) & ~3));
+  const float NEG_INF = __int_as_float(0xff800000);
+  for (int64_t row = int64_t(blockIdx.x) * ROWS_WARPS + warp; row < n_rows; row += int64_t(gridDim.x) * ROWS_WARPS) {
+    // slice every static input by this row's evidence codes
+    bool bad = false;
+    for (int k = lane; k < n_inputs; k += 32) {
+      const RowInputDev& I = inputs[k];
+      int b = 0;
+      for (int j = 0; j < I.n_ev; ++j) {
+        const int c = ev[int64_t(I.slot[j]) * ld + row];
+        bad |= (c == CBN_UNSEEN);
+        b += c * I.stride[j];
+      }
+      base[k] = bad ? 0 : b;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    if (!bad) {
+      for (int j = 0; j < n_steps; ++j) {
+        const RowStepDev& S = sst[j];
+        float* tout = temps + S.temp_off;
+        float mx = LOG ? NEG_INF : 0.0f;
+        for (int o = lane; o < S.out_size; o += 32) {
+          float acc = LOG ? NEG_INF : 0.0f;
+          for (int sv = 0; sv < S.sum_card; ++sv) {
+            float prod = LOG ? 0.0f : 1.0f;
+            for (int k = 0; k < S.n_in; ++k) {
+              const int id = S.in_id[k];
+              const float* src = id < n_inputs ? inputs[id].data + base[id] : temps + sst[id - n_inputs].temp_off;
+              const float x = src[__ldg(S.offsets + k * S.out_size + o) + sv * S.sum_stride[k]];
+              prod = LOG ? prod + x : prod * x;
+            }
+            if (LOG) {
+              const float hi = fmaxf(acc, prod), lo = fminf(acc, prod);
+              acc = (hi == NEG_INF) ? NEG_INF : hi + log1pf(expf(lo - hi));
+            } else {
+              acc += prod;
+            }
+          }
+          tout[o] = acc;
+          mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        __syncwarp();
+        if (j + 1 < n_steps) {
+          // keep the temporary in range: divide by its maximum (subtract it in log space)
+          if (LOG) {
+            if (mx != NEG_INF) for (int o = lane; o < S.out_size; o += 32) tout[o] -= mx;
+          } else if (mx > 0.0f) {
+            const float inv = 1.0f / mx;
+            for (int o = lane; o < S.out_size; o += 32) tout[o] *= inv;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // normalise the last temporary over the target and write the posterior row
+    const float* last = temps + sst[n_steps - 1].temp_off;
+    float z = 0.0f, mx = NEG_INF;
+    if (LOG && !bad) {
+      for (int t = lane; t < card_t; t += 32) mx = fmaxf(mx, last[t]);
+      mx = warp_max(mx);
+    }
+    for (int t = lane; t < card_t; t += 32) {
+      float v = 0.0f;
+      if (!bad) v = LOG ? (mx == NEG_INF ? 0.0f : expf(last[t] - mx)) : last[t];
+      z += v;
+    }
+    z = warp_sum(z);
+    const float inv = z > 0.0f ? 1.0f / z : 0.0f;
+    for (int t = lane; t < card_t; t += 32) {
+      float v = 0.0f;
+      if (!bad) v = LOG ? (mx == NEG_INF ? 0.0f : expf(last[t] - mx)) : last[t];
+      out[row * card_t + t] = v * inv;
+    }
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
+                                       const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps,
+                                       int32_t n_steps, int32_t flags, cbn_ve_plan** out) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: ctx is NULL");
+  if (!out || n_evidence < 0 || n_evidence > 255 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD ||
+      !inputs || n_inputs < 1 || n_inputs > ROWS_MAX_INPUTS || !steps || n_steps < 1 || n_steps > ROWS_MAX_STEPS)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: bad argument");
+  DeviceGuard g(ctx->device);
+  std::vector<RowInputDev> hi(n_inputs);
+  for (int k = 0; k < n_inputs; ++k) {
+    const cbn_row_input& I = inputs[k];
+    if (!I.data || I.n_ev < 0 || I.n_ev > GATHER_MAX_TABLE_EV || I.n_cells < 1 || I.n_cells > 0x7fffffffll)
+      return cbn_fail(ctx, CBN_ERR_INVALID, "row input %d: bad descriptor", k);
+    hi[k] = RowInputDev{};
+    hi[k].data = I.data; hi[k].n_cells = (int)I.n_cells; hi[k].n_ev = I.n_ev;
+    long long reach = 0;
+    for (int j = 0; j < I.n_ev; ++j) {
+      if (I.ev_slot[j] < 0 || I.ev_slot[j] >= n_evidence || I.ev_stride[j] < 0)
+        return cbn_fail(ctx, CBN_ERR_INVALID, "row input %d: bad evidence axis %d", k, j);
+      hi[k].slot[j] = (uint8_t)I.ev_slot[j];
+      hi[k].stride[j] = I.ev_stride[j];
+      reach += (long long)(ev_cards[I.ev_slot[j]] - 1) * I.ev_stride[j];
+    }
+    if (reach >= I.n_cells) return cbn_fail(ctx, CBN_ERR_INVALID, "row input %d: evidence strides leave the table", k);
+  }
+  std::vector<RowStepDev> hs(n_steps);
+  int temp = 0;
+  for (int j = 0; j < n_steps; ++j) {
+    const cbn_row_step& S = steps[j];
+    if (S.out_size < 1 || S.sum_card < 1 || S.n_in < 1 || S.n_in > CBN_MAX_CONTRACT_INPUTS || !S.offsets)
+      return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: bad descriptor", j);
+    hs[j] = RowStepDev{};
+    hs[j].offsets = S.offsets; hs[j].out_size = S.out_size; hs[j].sum_card = S.sum_card; hs[j].n_in = S.n_in;
+    hs[j].temp_off = temp;
+    for (int k = 0; k < S.n_in; ++k) {
+      if (S.in_id[k] < 0 || S.in_id[k] >= n_inputs + j)
+        return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: input %d refers to a later step", j, k);
+      hs[j].in_id[k] = S.in_id[k];
+      hs[j].sum_stride[k] = S.sum_stride[k];
+    }
+    temp += (S.out_size + 3) & ~3;
+  }
+  if (steps[n_steps - 1].out_size != card_t)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: the last step must produce card_t cells");
+  const size_t smem = size_t(n_steps) * sizeof(RowStepDev) + size_t(ROWS_WARPS) * (((n_inputs + 3) & ~3) + temp) * 4;
+  if (smem > 200 * 1024)
+    return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "per-row plan needs %zu bytes of shared memory per CTA (limit 200 KB)", smem);
+  cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
+  if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
+  p->device = ctx->device; p->kind = 1; p->n_evidence = n_evidence; p->card_t = card_t; p->n_out = 1; p->normalize_mask = 1;
+  p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
+  p->rows_n_inputs = n_inputs; p->rows_n_steps = n_steps; p->rows_temp_floats = temp; p->rows_flags = flags;
+  p->blob_bytes = smem;
+  cudaError_t e = cudaMalloc(&p->d_row_inputs, sizeof(RowInputDev) * n_inputs);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_row_inputs, hi.data(), sizeof(RowInputDev) * n_inputs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_row_steps, sizeof(RowStepDev) * n_steps);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_row_steps, hs.data(), sizeof(RowStepDev) * n_steps, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) { cbn_ve_plan_destroy(p); return cbn_fail(ctx, CBN_ERR_CUDA, "per-row plan upload: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return CBN_OK;
+}
+
+static int ve_run_rows(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, float* out, cudaStream_t s) {
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (p->blob_bytes + 1024)));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + ROWS_WARPS - 1) / ROWS_WARPS, int64_t(ctx->sm_count) * per_sm));
+  if (p->rows_flags & CBN_ROWS_LOG_SPACE)
+    ve_rows_kernel<true><<<blocks, ROWS_TPB, p->blob_bytes, s>>>((const RowInputDev*)p->d_row_inputs, p->rows_n_inputs,
+                                                                (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+                                                                ev, ld, n_rows, p->card_t, out);
+  else
+    ve_rows_kernel<false><<<blocks, ROWS_TPB, p->blob_bytes, s>>>((const RowInputDev*)p->d_row_inputs, p->rows_n_inputs,
+                                                                 (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+                                                                 ev, ld, n_rows, p->card_t, out);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
 extern "C" int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
                                 int64_t n_rows, float* posterior, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes: ctx is NULL");
@@ -742,12 +955,14 @@ extern "C" int cbn_ve_run_codes(cbn_ctx* ctx, const cbn_ve_plan* plan, const uin
   if (rc) return rc;
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
+  if (plan->kind == 1) return ve_run_rows(ctx, plan, ev_codes, ld, n_rows, posterior, (cudaStream_t)stream);
   return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, outs, (cudaStream_t)stream);
 }
 
 extern "C" int cbn_ve_run_codes_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld,
                                       int64_t n_rows, float* const* posteriors, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_multi: ctx is NULL");
+  if (plan && plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_multi: not a gather plan");
   GatherOuts outs{};
   int rc = check_run_args(ctx, "cbn_ve_run_codes_multi", plan, ev_codes, ld, n_rows, posteriors, &outs);
   if (rc) return rc;
@@ -762,6 +977,7 @@ extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float
   if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && (!ev_cols || !domains)))
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: bad argument");
   if (plan->n_out != 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: fused plans take codes (cbn_ve_run_codes_multi)");
+  if (plan->kind != 0) return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: per-row plans take codes (encode with cbn_encode_f32)");
   if (plan->n_evidence > CBN_MAX_EVIDENCE_PTRS)
     return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: more than %d evidence columns; encode them and use cbn_ve_run_codes", CBN_MAX_EVIDENCE_PTRS);
   if (plan->card_t > GATHER_MAX_CT)
@@ -826,7 +1042,7 @@ extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, cons
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
   if (!plan || !posterior_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
-  if (plan->n_out != 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: fused plans are device-side only");
+  if (plan->n_out != 1 || plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: fused and per-row plans are device-side only");
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
   const int64_t chunk = 1 << 20;  // rows per chunk

@@ -6,7 +6,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from ..base.inference import BaseInference
-from ..ve import FusedPlan, QueryPlan, VECompiler
+from ..ve import FusedPlan, QueryPlan, RowPlan, VECompiler
 
 
 class ExactInference(BaseInference):
@@ -20,7 +20,10 @@ class ExactInference(BaseInference):
         self.normalization = (config or {}).get("normalization", "row")
         if self.normalization not in ("row", "global_max"):
             raise ValueError(f"normalization must be 'row' or 'global_max', got {self.normalization!r}")
-        self._budget = {k: int(config[k]) for k in ("table_budget_cells", "merge_budget_cells") if config and k in config}
+        self._budget = {k: int(config[k]) for k in ("table_budget_cells", "merge_budget_cells", "row_temp_floats")
+                        if config and k in config}
+        if config and "log_space" in config:
+            self._budget["log_space"] = bool(config["log_space"])
 
     def bind(self, tables):
         """Attach the fitted network tables (called by BayesianNetwork after every fit)."""

@@ -50,6 +50,7 @@ class PlanStats:
     contraction_madds: int = 0
     final_tables: List[Tuple[Tuple[int, ...], int]] = field(default_factory=list)
     support_unchecked: bool = False
+    per_row_hidden: int = 0                      # hidden variables left to the per-row executor (0 = gather plan)
     relevant_evidence: List[int] = field(default_factory=list)
 
 
@@ -171,15 +172,95 @@ class FusedPlan:
         return list(outs)
 
 
+class RowPlan:
+    """A query whose evidence boundary is too large to tabulate: static tables for what could be eliminated at
+    compile time + a per-row schedule of product / sum-out steps (``cbn_ve_plan_create_rows``)."""
+
+    def __init__(self, tables_owner, target: int, evidence: List[int], card_t: int, inputs: List[Factor],
+                 steps: List[dict], offsets: torch.Tensor, stats: PlanStats, log_space: bool):
+        self.owner = tables_owner
+        self.ctx = tables_owner.ctx
+        self.device = tables_owner.device
+        self.target = target
+        self.evidence = list(evidence)
+        self.card_t = card_t
+        self.inputs = inputs            # keep the tables alive
+        self.offsets = offsets
+        self.stats = stats
+        self.log_space = log_space
+        self.handle = None
+        cards = tables_owner.cards
+        slot = {v: i for i, v in enumerate(self.evidence)}
+        Eset = set(self.evidence)
+        ins = (N.RowInput * len(inputs))()
+        for k, f in enumerate(inputs):
+            ins[k].data = f.tensor.data_ptr()
+            ins[k].n_cells = f.tensor.numel()
+            stride, j = 1, 0
+            ev_axes = []
+            for v in reversed(f.scope):
+                if v in Eset:
+                    ev_axes.append((slot[v], stride))
+                stride *= cards[v]
+            ins[k].n_ev = len(ev_axes)
+            for j, (sl, st) in enumerate(ev_axes):
+                ins[k].ev_slot[j] = sl
+                ins[k].ev_stride[j] = st
+        sts = (N.RowStep * len(steps))()
+        for j, st in enumerate(steps):
+            sts[j].out_size = st["out_size"]
+            sts[j].sum_card = st["sum_card"]
+            sts[j].n_in = len(st["in_id"])
+            for k, (i, ss) in enumerate(zip(st["in_id"], st["sum_stride"])):
+                sts[j].in_id[k] = i
+                sts[j].sum_stride[k] = ss
+            sts[j].offsets = offsets.data_ptr() + 4 * st["offsets_at"]
+        ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
+        h = C.c_void_p()
+        N.check(N.lib().cbn_ve_plan_create_rows(self.ctx.handle, len(self.evidence), ev_cards, card_t, ins, len(inputs), sts,
+                                                len(steps), N.ROWS_LOG_SPACE if log_space else 0, C.byref(h)), self.ctx.handle)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                N.lib().cbn_ve_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def algorithmic_bytes_per_row(self) -> int:
+        return len(self.stats.relevant_evidence) + 4 * self.card_t
+
+    def run_codes(self, ev_codes: torch.Tensor, n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert ev_codes.dtype == torch.uint8 and ev_codes.is_cuda
+        if out is None:
+            out = torch.empty((n_rows, self.card_t), dtype=torch.float32, device=self.device)
+        ld = ev_codes.stride(0) if ev_codes.dim() == 2 else 0
+        N.check(N.lib().cbn_ve_run_codes(self.ctx.handle, self.handle, ev_codes.data_ptr(), ld, int(n_rows),
+                                         out.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
+        return out
+
+    def run_f32(self, ev_cols: Sequence[torch.Tensor], n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Float evidence columns: encoded on the device first (unseen values -> CBN_UNSEEN -> zero rows)."""
+        ld = (max(n_rows, 1) + 15) // 16 * 16
+        codes = torch.empty((max(len(self.evidence), 1), ld), dtype=torch.uint8, device=self.device)
+        for e, (v, col) in enumerate(zip(self.evidence, ev_cols)):
+            self.owner.encode(col, v, codes[e])
+        return self.run_codes(codes, n_rows, out)
+
+
 class VECompiler:
     """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
 
     def __init__(self, tables, table_budget_cells: int = 1 << 28, merge_budget_cells: int = 1 << 24,
-                 check_support: bool = True):
+                 check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False):
         self.t = tables
         self.table_budget = int(table_budget_cells)
         self.merge_budget = int(merge_budget_cells)
         self.check_support = check_support
+        self.row_temp_floats = int(row_temp_floats)     # per-row temporaries of the per-row executor (shared memory)
+        self.log_space = bool(log_space)
         self._cache: Dict[tuple, QueryPlan] = {}
         self._has_zero: Dict[int, bool] = {}
 
@@ -298,7 +379,7 @@ class VECompiler:
             rel_ev |= {v for v in f.scope if v in Eset}
         stats.relevant_evidence = [v for v in E if v in rel_ev]
 
-        finals = self._eliminate(main, [v for v in hidden if find(v) == comp_t], sort_scope, stats, dry, T)
+        finals, left = self._eliminate(main, [v for v in hidden if find(v) == comp_t], sort_scope, stats, dry, T, partial=True)
 
         # support of the dropped part: a row whose (irrelevant) evidence has probability zero is all zeros in
         # the oracle's convention; only factors that can be zero matter
@@ -330,6 +411,17 @@ class VECompiler:
                     except PlanTooLarge:
                         stats.support_unchecked = True
 
+        if left:
+            # the boundary is too large to tabulate: the rest of the hidden variables is eliminated per row
+            stats.per_row_hidden = len(left)
+            stats.final_tables = [(tuple(f.scope), f.size(cards)) for f in finals]
+            if self.log_space and not dry:
+                finals = [Factor(f.scope, torch.log(f.tensor)) for f in finals]
+            plan = self._row_plan(T, E, finals, left, stats, dry)
+            if dry:
+                return stats
+            self._cache[key] = plan
+            return plan
         finals = self._merge_finals(finals, sort_scope, stats, dry, T)
         stats.final_tables = [(tuple(f.scope), f.size(cards)) for f in finals]
         if dry:
@@ -347,7 +439,10 @@ class VECompiler:
         self._cache[key] = plan
         return plan
 
-    def _eliminate(self, factors: List[Factor], hidden: List[int], sort_scope, stats: PlanStats, dry: bool, T: int):
+    def _eliminate(self, factors: List[Factor], hidden: List[int], sort_scope, stats: PlanStats, dry: bool, T: int,
+                   partial: bool = False):
+        """Evidence-symbolic elimination.  With ``partial`` the loop stops when the cheapest step exceeds the table
+        budget and returns ``(factors, remaining_hidden)`` for the per-row executor instead of raising."""
         cards = self.t.cards
         factors = list(factors)
         hidden = list(hidden)
@@ -369,6 +464,8 @@ class VECompiler:
                 c = cells(scope)
                 if best_cost is None or c < best_cost:
                     best, best_cost, best_scope = v, c, scope
+            if best_cost > self.table_budget and partial:
+                return factors, hidden
             if best_cost > self.table_budget:
                 raise PlanTooLarge(
                     f"eliminating the cheapest hidden variable needs a table of {best_cost} cells "
@@ -391,7 +488,95 @@ class VECompiler:
             stats.max_table_cells = max(stats.max_table_cells, best_cost)
             stats.contraction_madds += best_cost * cards[v] * len(touching)
             factors.append(self._contract(touching, out_scope, v, dry))
-        return factors
+        return (factors, []) if partial else factors
+
+    # ---------------------------------------------------------------- per-row schedule
+    def _row_plan(self, T: int, E: List[int], statics: List[Factor], hidden: List[int], stats: PlanStats, dry: bool):
+        """Schedule the elimination of ``hidden`` per row: evidence axes of the static tables are sliced by the
+        row's codes, so only hidden axes (and the target) count towards the size of a temporary."""
+        import numpy as np
+
+        cards = self.t.cards
+        Eset = set(E)
+        n_in = len(statics)
+
+        def strides_of(scope):
+            st, s = {}, 1
+            for v in reversed(scope):
+                st[v] = s
+                s *= cards[v]
+            return st
+
+        # row factors: (id, free scope, strides over the free axes)
+        rf = []
+        for k, f in enumerate(statics):
+            st = strides_of(f.scope)
+            free = [v for v in f.scope if v not in Eset]
+            rf.append((k, free, {v: st[v] for v in free}))
+        steps, off_chunks, off_at, temp_total = [], [], 0, 0
+
+        def emit(inputs, out_scope, sum_var):
+            nonlocal off_at, temp_total
+            out_shape = [cards[v] for v in out_scope]
+            out_size = int(np.prod(out_shape)) if out_shape else 1
+            offs = np.zeros((len(inputs), out_size), dtype=np.int64)
+            grids = np.indices(out_shape).reshape(len(out_scope), -1) if out_scope else np.zeros((0, 1), dtype=np.int64)
+            for k, (_, _, st) in enumerate(inputs):
+                for d, v in enumerate(out_scope):
+                    if v in st:
+                        offs[k] += grids[d] * st[v]
+            steps.append({"out_size": out_size, "sum_card": cards[sum_var] if sum_var is not None else 1,
+                          "in_id": [i for i, _, _ in inputs],
+                          "sum_stride": [st.get(sum_var, 0) if sum_var is not None else 0 for _, _, st in inputs],
+                          "offsets_at": off_at})
+            off_chunks.append(offs.astype(np.int32).reshape(-1))
+            off_at += offs.size
+            temp_total += (out_size + 3) // 4 * 4
+            stats.contraction_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
+            if temp_total > self.row_temp_floats:
+                raise PlanTooLarge(
+                    f"per-row elimination needs {temp_total} floats of temporaries per row (budget {self.row_temp_floats}): "
+                    "the hidden part of this query has too large an induced width for exact inference")
+            return (n_in + len(steps) - 1, list(out_scope), strides_of(out_scope))
+
+        def size_of(scope):
+            s = 1
+            for v in scope:
+                s *= cards[v]
+            return s
+
+        hidden = list(hidden)
+        while hidden:
+            best = None
+            for v in hidden:
+                sc = set()
+                for _, free, _ in rf:
+                    if v in free:
+                        sc |= set(free)
+                sc.discard(v)
+                c = size_of(sc)
+                if best is None or c < best[0]:
+                    best = (c, v, sc)
+            _, v, sc = best
+            hidden.remove(v)
+            touching = [f for f in rf if v in f[1]]
+            rf = [f for f in rf if v not in f[1]]
+            out_scope = sorted(sc, key=lambda a: (a == T, a))
+            while len(touching) > N.MAX_CONTRACT_INPUTS:       # pre-multiply the two smallest
+                touching.sort(key=lambda f: size_of(f[1]))
+                a, b = touching[0], touching[1]
+                psc = sorted(set(a[1]) | set(b[1]), key=lambda x: (x == T, x))
+                touching = touching[2:] + [emit([a, b], psc, None)]
+            rf.append(emit(touching, out_scope, v))
+            stats.n_steps += 1
+        # final product over what is left (free scope is empty or [T])
+        while len(rf) > N.MAX_CONTRACT_INPUTS:
+            rf = rf[N.MAX_CONTRACT_INPUTS:] + [emit(rf[:N.MAX_CONTRACT_INPUTS], [T], None)]
+        emit(rf, [T], None)
+        if dry:
+            return None
+        offsets = torch.from_numpy(np.concatenate(off_chunks)).to(self.t.device)
+        return RowPlan(self.t, T, E, cards[T], statics, steps, offsets, stats, self.log_space)
 
     def _merge_finals(self, finals: List[Factor], sort_scope, stats: PlanStats, dry: bool, T: int) -> List[Factor]:
         """Multiply final tables together while the product stays within the merge budget: fewer gathers

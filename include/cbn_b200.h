@@ -183,6 +183,33 @@ CBN_API void cbn_ve_plan_destroy(cbn_ve_plan* plan);
 CBN_API int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_ve_plan** out);
 CBN_API int cbn_ve_plan_outputs(const cbn_ve_plan* plan);
 
+/* Per-row elimination plan: used when the evidence boundary of the target's component is too large to tabulate.
+ * Whatever could be eliminated at compile time arrives as static `inputs` (tables over evidence axes and hidden
+ * axes); the remaining hidden variables are summed out PER ROW by a fused schedule of product/sum-out steps whose
+ * intermediates live in shared memory (one warp per row).  Step j produces a temporary of out_size cells:
+ *     tmp_j[o] = sum_{s < sum_card} prod_k in_k[ offsets[k][o] + s * sum_stride[k] ]
+ * where in_k is a static input (sliced by the row's evidence codes) or an earlier temporary; the last step has
+ * out_size == card_t and is normalised over the target.  flags bit 0: run in log space (log-sum-exp). */
+#define CBN_ROWS_LOG_SPACE 1
+typedef struct cbn_row_input {
+  const float* data; /* device */
+  int64_t n_cells;
+  int32_t n_ev;
+  int32_t ev_slot[CBN_MAX_CONTRACT_DIMS];
+  int32_t ev_stride[CBN_MAX_CONTRACT_DIMS];
+} cbn_row_input;
+typedef struct cbn_row_step {
+  int32_t out_size;
+  int32_t sum_card;
+  int32_t n_in;
+  int32_t in_id[CBN_MAX_CONTRACT_INPUTS];      /* < n_inputs: static input, else temporary of step in_id - n_inputs */
+  int32_t sum_stride[CBN_MAX_CONTRACT_INPUTS];
+  const int32_t* offsets;                      /* device int32 [n_in][out_size] */
+} cbn_row_step;
+CBN_API int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
+                            const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps, int32_t n_steps,
+                            int32_t flags, cbn_ve_plan** out);
+
 /* evidence as codes: column e of the plan's evidence list at ev_codes + e * ld.
  * posterior: device float[n_rows, card_t], rows sum to 1 (all zeros when the evidence
  * has probability 0 or contains CBN_UNSEEN). */

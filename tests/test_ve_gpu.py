@@ -212,6 +212,54 @@ def test_fused_multi_target_launch_matches_single_plans():
         infer.fused_plan(["HYPOVOLEMIA", "VENTLUNG"], synth.ALARM_EVIDENCE)
 
 
+def test_per_row_executor_matches_oracle():
+    """A small table budget forces the per-row elimination schedule (linear-rescaled and log-space)."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import bind_inference, tables_from_spec
+    from continuousbayesiannetwork_b200.ve import RowPlan
+
+    spec = synth.alarm()
+    codes = synth.sample_forward_numpy(spec, 31, 0, 1031)
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    ev = codes[ids].T.copy()
+    ev[5, 3] = 255                                              # unseen value -> zero row
+    net = _net(spec)
+    for log_space in (False, True):
+        t = tables_from_spec(spec, DEV)
+        t.set_cond_tables(spec.cpts)
+        infer = bind_inference(t, table_budget_cells=1 << 10, log_space=log_space)
+        for target in ("HYPOVOLEMIA", "VENTLUNG", "CATECHOL"):
+            plan = infer.plan(target, synth.ALARM_EVIDENCE)
+            assert isinstance(plan, RowPlan) and plan.stats.per_row_hidden > 0
+            got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
+            ok = np.ones(ev.shape[0], bool); ok[5] = False
+            want = O.ve_posterior(net, spec.names.index(target), ids, ev[ok], dtype=torch.float64)
+            np.testing.assert_allclose(got[ok], want, rtol=2e-5 if log_space else RTOL, atol=1e-30)
+            assert np.all(got[5] == 0)
+            # the float-valued entry point encodes and runs the same plan
+            cols = [torch.tensor(ev[:, i].astype(np.float32), device=DEV) for i in range(len(ids))]
+            cols[3][5] = 1234.0
+            got32 = plan.run_f32(cols, ev.shape[0]).cpu().numpy()
+            assert np.array_equal(got32, got)
+    # naive-Bayes shape: one hidden cause with 40 observed children: the boundary (3^40) cannot be tabulated
+    rng = np.random.default_rng(12)
+    n_child = 40
+    names = ["cause", "t"] + [f"c{i:02d}" for i in range(n_child)]
+    cards = [4, 3] + [3] * n_child
+    parents = [[], [0]] + [[0]] * n_child
+    spec = synth.NetSpec(names, cards, parents, synth._dirichlet_cpts(rng, cards, parents, 0.5))
+    t = tables_from_spec(spec, DEV)
+    t.set_cond_tables(spec.cpts)
+    infer = bind_inference(t, table_budget_cells=1 << 16)
+    codes = synth.sample_forward_numpy(spec, 2, 0, 513)
+    evn = names[2:]
+    plan = infer.plan("t", evn)
+    assert isinstance(plan, RowPlan)
+    got = plan.run_codes(_codes_matrix(codes[2:].T), 513).cpu().numpy()
+    want = O.ve_posterior(_net(spec), 1, list(range(2, 2 + n_child)), codes[2:].T, dtype=torch.float64)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+
+
 def test_fit_then_infer_end_to_end_on_fitted_tables():
     """Config-2 shape end to end: sample -> count -> CPTs -> compile -> query, checked against the oracle
     run on the oracle's own tables (counts bit-exact, so the CPTs agree to the last bit of the division)."""
