@@ -79,13 +79,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// exact redo of one family for the 8 samples of a thread (a code >= 128 was seen: cardinality > 128 or CBN_UNSEEN)
-__device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent, int e0, int e1, const unsigned char* st,
+// exact redo of one family for the 8 samples of a lane (a code >= 128 was seen: cardinality > 128 or CBN_UNSEEN)
+__device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent, int n_ent, const unsigned char* st,
                                                 uint32_t* tb, uint32_t nc) {
   for (int half = 0; half < 2; ++half) {
     uint32_t idx[4] = {0, 0, 0, 0};
     uint32_t badrow = 0;
-    for (int e = e0; e < e1; ++e) {
+    for (int e = 0; e < n_ent; ++e) {
       const uint32_t v = ent[e];
       const uint32_t w = *reinterpret_cast<const uint32_t*>(st + (v & 0xffffu) + 4 * half);
       const uint32_t s = v >> 16;
@@ -102,10 +102,89 @@ __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent
   }
 }
 
+// One warp, one family, one staged tile: the family's column offsets and strides sit in registers (NLO byte-lane
+// variables, NHI 16-bit-lane variables, both compile-time), each lane walks the tile 8 samples at a time.
+// NLO < 0 selects the generic (runtime trip count) body.
+template <int NLO, int NHI>
+__device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ ent, int n_lo, int n_hi,
+                                                  const unsigned char* __restrict__ tile, uint32_t* __restrict__ tb,
+                                                  uint32_t nc, int lane) {
+  constexpr bool GENERIC = NLO < 0;
+  constexpr int RLO = GENERIC ? 1 : (NLO > 0 ? NLO : 1), RHI = GENERIC ? 1 : (NHI > 0 ? NHI : 1);
+  uint32_t off_lo[RLO], s_lo[RLO], off_hi[RHI], s_hi[RHI];
+  if (!GENERIC) {
+#pragma unroll
+    for (int k = 0; k < NLO; ++k) { off_lo[k] = ent[k] & 0xffffu; s_lo[k] = ent[k] >> 16; }
+#pragma unroll
+    for (int k = 0; k < NHI; ++k) { off_hi[k] = ent[NLO + k] & 0xffffu; s_hi[k] = ent[NLO + k] >> 16; }
+  }
+#pragma unroll 2
+  for (int wofs = lane * 8; wofs < TILE; wofs += 32 * 8) {
+    const unsigned char* st = tile + wofs;
+    uint32_t a8x = 0, a8y = 0, aEx = 0, aOx = 0, aEy = 0, aOy = 0, any = 0;
+    if (GENERIC) {
+      for (int k = 0; k < n_lo; ++k) {
+        const uint32_t v = ent[k];
+        const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
+        any |= w.x | w.y;
+        a8x += w.x * (v >> 16);
+        a8y += w.y * (v >> 16);
+      }
+      for (int k = n_lo; k < n_lo + n_hi; ++k) {
+        const uint32_t v = ent[k];
+        const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
+        const uint32_t s = v >> 16;
+        any |= w.x | w.y;
+        aEx += (w.x & 0x00ff00ffu) * s; aOx += ((w.x >> 8) & 0x00ff00ffu) * s;
+        aEy += (w.y & 0x00ff00ffu) * s; aOy += ((w.y >> 8) & 0x00ff00ffu) * s;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NLO; ++k) {
+        const uint2 w = *reinterpret_cast<const uint2*>(st + off_lo[k]);
+        any |= w.x | w.y;
+        a8x += w.x * s_lo[k];                                 // 4 x 8-bit lanes, no carry between them
+        a8y += w.y * s_lo[k];
+      }
+#pragma unroll
+      for (int k = 0; k < NHI; ++k) {
+        const uint2 w = *reinterpret_cast<const uint2*>(st + off_hi[k]);
+        any |= w.x | w.y;
+        aEx += (w.x & 0x00ff00ffu) * s_hi[k];                 // samples 0, 2 in 16-bit lanes
+        aOx += ((w.x >> 8) & 0x00ff00ffu) * s_hi[k];          // samples 1, 3
+        aEy += (w.y & 0x00ff00ffu) * s_hi[k];
+        aOy += ((w.y >> 8) & 0x00ff00ffu) * s_hi[k];
+      }
+    }
+    if (any & 0x80808080u) {
+      count_family_exact(ent, n_lo + n_hi, st, tb, nc);
+    } else if ((!GENERIC && NHI == 0) || (GENERIC && n_hi == 0)) {
+      // byte-lane only: the index is a byte and the table is padded to 256 cells -> no clamp needed
+      atomicAdd(tb + (a8x & 0xffu), 1u);
+      atomicAdd(tb + ((a8x >> 8) & 0xffu), 1u);
+      atomicAdd(tb + ((a8x >> 16) & 0xffu), 1u);
+      atomicAdd(tb + (a8x >> 24), 1u);
+      atomicAdd(tb + (a8y & 0xffu), 1u);
+      atomicAdd(tb + ((a8y >> 8) & 0xffu), 1u);
+      atomicAdd(tb + ((a8y >> 16) & 0xffu), 1u);
+      atomicAdd(tb + (a8y >> 24), 1u);
+    } else {
+      atomicAdd(tb + min((a8x & 0xffu) + (aEx & 0xffffu), nc), 1u);      // cell nc is the family's spare
+      atomicAdd(tb + min(((a8x >> 8) & 0xffu) + (aOx & 0xffffu), nc), 1u);
+      atomicAdd(tb + min(((a8x >> 16) & 0xffu) + (aEx >> 16), nc), 1u);
+      atomicAdd(tb + min((a8x >> 24) + (aOx >> 16), nc), 1u);
+      atomicAdd(tb + min((a8y & 0xffu) + (aEy & 0xffffu), nc), 1u);
+      atomicAdd(tb + min(((a8y >> 8) & 0xffu) + (aOy & 0xffffu), nc), 1u);
+      atomicAdd(tb + min(((a8y >> 16) & 0xffu) + (aEy >> 16), nc), 1u);
+      atomicAdd(tb + min((a8y >> 24) + (aOy >> 16), nc), 1u);
+    }
+  }
+}
+
 // shared memory: [counters][family headers][entry stream][stage 0][stage 1]
 __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
-    const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint2* __restrict__ famhdr,
+    const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint4* __restrict__ famhdr,
     const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
@@ -115,10 +194,10 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   const int64_t xstride = gridDim.x / n_groups;
   const TileGroup G = groups[g];
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
-  const size_t hdr_off = (size_t(G.n_cells) * 4 + 7) & ~size_t(7);
-  uint2* s_hdr = reinterpret_cast<uint2*>(smem + hdr_off);
-  uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem + hdr_off + size_t(G.n_fams) * 8);
-  unsigned char* stage = smem + ((hdr_off + size_t(G.n_fams) * 8 + size_t(G.n_entries) * 4 + 127) & ~size_t(127));
+  const size_t hdr_off = (size_t(G.n_cells) * 4 + 15) & ~size_t(15);
+  uint4* s_hdr = reinterpret_cast<uint4*>(smem + hdr_off);
+  uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem + hdr_off + size_t(G.n_fams) * 16);
+  unsigned char* stage = smem + ((hdr_off + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127));
   const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
   for (int i = threadIdx.x; i < G.n_entries; i += blockDim.x) s_ent[i] = entries[G.ent_start + i];
   for (int i = threadIdx.x; i < G.n_fams; i += blockDim.x) s_hdr[i] = famhdr[G.fam_start + i];
@@ -143,70 +222,29 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   int buf = 0;
   uint32_t phase0 = 0, phase1 = 0;
   if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
-  const uint32_t wofs = threadIdx.x * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_fams = G.n_fams;
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
     if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
     if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
-    const unsigned char* st = stage + size_t(buf) * tile_bytes + wofs;
-    const uint32_t* ep = s_ent;
-#pragma unroll 1
-    for (int f = 0; f < n_fams; ++f) {
-      const uint2 hdr = s_hdr[f];                           // x: (table offset << 16) | n_cells, y: n_lo | n_hi << 8
-      const uint32_t nc = hdr.x & 0xffffu;                  // cell nc is the family's spare (never flushed)
-      uint32_t* tb = tbl + (hdr.x >> 16);
-      const int n_lo = hdr.y & 0xffu, n_hi = (hdr.y >> 8) & 0xffu;
-      const uint32_t* e0 = ep;
-      uint32_t a8x = 0, a8y = 0, any = 0;
-#pragma unroll 1
-      for (int k = 0; k < n_lo; ++k) {
-        const uint32_t v = *ep++;
-        const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
-        const uint32_t s = v >> 16;
-        any |= w.x | w.y;
-        a8x += w.x * s;                                     // 4 x 8-bit lanes, no carry between them
-        a8y += w.y * s;
-      }
-      if (n_hi == 0) {
-        if (any & 0x80808080u) {
-          count_family_exact(s_ent, int(e0 - s_ent), int(ep - s_ent), st, tb, nc);
-        } else {
-          atomicAdd(tb + min(a8x & 0xffu, nc), 1u);
-          atomicAdd(tb + min((a8x >> 8) & 0xffu, nc), 1u);
-          atomicAdd(tb + min((a8x >> 16) & 0xffu, nc), 1u);
-          atomicAdd(tb + min(a8x >> 24, nc), 1u);
-          atomicAdd(tb + min(a8y & 0xffu, nc), 1u);
-          atomicAdd(tb + min((a8y >> 8) & 0xffu, nc), 1u);
-          atomicAdd(tb + min((a8y >> 16) & 0xffu, nc), 1u);
-          atomicAdd(tb + min(a8y >> 24, nc), 1u);
-        }
-      } else {
-        uint32_t aEx = 0, aOx = 0, aEy = 0, aOy = 0;
-#pragma unroll 1
-        for (int k = 0; k < n_hi; ++k) {
-          const uint32_t v = *ep++;
-          const uint2 w = *reinterpret_cast<const uint2*>(st + (v & 0xffffu));
-          const uint32_t s = v >> 16;
-          any |= w.x | w.y;
-          aEx += (w.x & 0x00ff00ffu) * s;                   // samples 0, 2 in 16-bit lanes
-          aOx += ((w.x >> 8) & 0x00ff00ffu) * s;            // samples 1, 3
-          aEy += (w.y & 0x00ff00ffu) * s;
-          aOy += ((w.y >> 8) & 0x00ff00ffu) * s;
-        }
-        if (any & 0x80808080u) {
-          count_family_exact(s_ent, int(e0 - s_ent), int(ep - s_ent), st, tb, nc);
-        } else {
-          atomicAdd(tb + min((a8x & 0xffu) + (aEx & 0xffffu), nc), 1u);
-          atomicAdd(tb + min(((a8x >> 8) & 0xffu) + (aOx & 0xffffu), nc), 1u);
-          atomicAdd(tb + min(((a8x >> 16) & 0xffu) + (aEx >> 16), nc), 1u);
-          atomicAdd(tb + min((a8x >> 24) + (aOx >> 16), nc), 1u);
-          atomicAdd(tb + min((a8y & 0xffu) + (aEy & 0xffffu), nc), 1u);
-          atomicAdd(tb + min(((a8y >> 8) & 0xffu) + (aOy & 0xffffu), nc), 1u);
-          atomicAdd(tb + min(((a8y >> 16) & 0xffu) + (aEy >> 16), nc), 1u);
-          atomicAdd(tb + min((a8y >> 24) + (aOy >> 16), nc), 1u);
-        }
+    const unsigned char* tile = stage + size_t(buf) * tile_bytes;
+    // family-stationary: each warp takes whole families, so the per-family metadata is loop invariant
+    for (int f = warp; f < n_fams; f += COUNT_TPB / 32) {
+      const uint4 hdr = s_hdr[f];        // x: table offset, y: n_cells, z: n_lo | n_hi << 8, w: first entry
+      uint32_t* tb = tbl + hdr.x;
+      const uint32_t nc = hdr.y;
+      const int n_lo = hdr.z & 0xffu, n_hi = (hdr.z >> 8) & 0xffu;
+      const uint32_t* ent = s_ent + hdr.w;
+      switch (hdr.z) {
+#define CBN_CASE(LO, HI) case (LO) | ((HI) << 8): count_family_tile<LO, HI>(ent, n_lo, n_hi, tile, tb, nc, lane); break;
+        CBN_CASE(1, 0) CBN_CASE(2, 0) CBN_CASE(3, 0) CBN_CASE(4, 0) CBN_CASE(5, 0) CBN_CASE(6, 0)
+        CBN_CASE(1, 1) CBN_CASE(2, 1) CBN_CASE(3, 1) CBN_CASE(4, 1)
+        CBN_CASE(1, 2) CBN_CASE(2, 2) CBN_CASE(3, 2) CBN_CASE(4, 2)
+        CBN_CASE(1, 3) CBN_CASE(2, 3) CBN_CASE(3, 3) CBN_CASE(4, 3)
+#undef CBN_CASE
+        default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, tb, nc, lane); break;
       }
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
@@ -214,10 +252,10 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   }
   // flush the private tables into the caller's int64 tables
   for (int f = 0; f < n_fams; ++f) {
-    const uint32_t h = s_hdr[f].x;
-    const int nc = int(h & 0xffffu);
+    const uint4 hdr = s_hdr[f];
+    const int nc = int(hdr.y);
     unsigned long long* dst = counts + goff[G.fam_start + f];
-    const uint32_t* tb = tbl + (h >> 16);
+    const uint32_t* tb = tbl + hdr.x;
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const uint32_t v = tb[c];
       if (v) atomicAdd(dst + c, (unsigned long long)v);
@@ -292,7 +330,7 @@ struct cbn_count_plan {
   TileGroup* d_groups = nullptr;
   int* d_gcols = nullptr;
   uint32_t* d_entries = nullptr;
-  uint2* d_famhdr = nullptr;
+  uint4* d_famhdr = nullptr;
   // direct kernel (tail + large families): small families grouped by the same clustering, large ones at the end
   int n_small = 0, n_large = 0;
   size_t direct_smem = 0;
@@ -343,13 +381,14 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       int seed = small[cursor];
       std::vector<int> members{seed};
       std::set<int> cols(fams[seed].var, fams[seed].var + fams[seed].n_vars);
-      int64_t gcells = cells[seed] + 1;            // + one spare cell per family (out-of-range updates land there)
+      auto alloc_of = [&](int f) { return std::max<int64_t>(cells[f] + 1, 256); };   // upper bound of the shared-memory cells a family takes
+      int64_t gcells = alloc_of(seed);
       int gentries = fams[seed].n_vars;
       used[seed] = 1; --left;
       while (left > 0 && (int)members.size() < MAX_GROUP_FAMS) {
         int best = -1, best_new = 1 << 30, best_shared = -1;
         for (int f : small) {
-          if (used[f] || gcells + cells[f] + 1 > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
+          if (used[f] || gcells + alloc_of(f) > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
               gentries + fams[f].n_vars > MAX_GROUP_ENTRIES) continue;
           int nnew = 0, shared = 0;
           for (int j = 0; j < fams[f].n_vars; ++j) (cols.count(fams[f].var[j]) ? shared : nnew)++;
@@ -359,7 +398,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         if (best < 0) break;
         members.push_back(best);
         for (int j = 0; j < fams[best].n_vars; ++j) cols.insert(fams[best].var[j]);
-        gcells += cells[best] + 1;
+        gcells += alloc_of(best);
         gentries += fams[best].n_vars;
         used[best] = 1; --left;
       }
@@ -375,7 +414,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   std::vector<TileGroup> h_groups;
   std::vector<int> h_gcols;
   std::vector<uint32_t> h_entries;
-  std::vector<uint2> h_famhdr;
+  std::vector<uint4> h_famhdr;
   std::vector<long long> h_goff;       // shared by both kernels: record order = group order, then large families
   std::vector<FamRec> h_recs;
   std::vector<int> h_group_start{0};
@@ -394,7 +433,8 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       fr.n_vars = F.n_vars;
       // strides, node fastest; walk from the node backwards: byte lanes while the partial index stays < 256
       int64_t st = 1, reach = 0;
-      int n_lo = 0, n_hi = 0;
+      int n_lo = 0, n_hi = 0, fam_alloc = 0;
+      const int ent_first = (int)h_entries.size() - G.ent_start;
       for (int j = F.n_vars - 1; j >= 0; --j) {
         fr.var[j] = F.var[j];
         fr.stride[j] = (int32_t)st;
@@ -404,10 +444,11 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         h_entries.push_back((uint32_t(st) << 16) | uint32_t(local * TILE));
         st *= F.card[j];
       }
-      h_famhdr.push_back(make_uint2((uint32_t(off) << 16) | uint32_t(cells[f]), uint32_t(n_lo) | (uint32_t(n_hi) << 8)));
+      h_famhdr.push_back(make_uint4(uint32_t(off), uint32_t(cells[f]), uint32_t(n_lo) | (uint32_t(n_hi) << 8), uint32_t(ent_first)));
+      fam_alloc = n_hi == 0 ? 256 : (int)cells[f] + 1;   // byte-lane families: any byte is in range; others: one spare cell
       h_recs.push_back(fr);
       h_goff.push_back(F.table_offset);
-      off += (int)cells[f] + 1;
+      off += fam_alloc;
       off_direct += (int)cells[f];
     }
     G.n_entries = (int)h_entries.size() - G.ent_start;
@@ -415,7 +456,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
     h_group_start.push_back((int)h_recs.size());
-    size_t s = ((((size_t(off) * 4 + 7) & ~size_t(7)) + size_t(G.n_fams) * 8 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    size_t s = ((((size_t(off) * 4 + 15) & ~size_t(15)) + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
     tile_smem = std::max(tile_smem, s);
     direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off_direct) * 4);
   }
