@@ -102,13 +102,18 @@ __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent
   }
 }
 
+__device__ __forceinline__ void red_inc(uint32_t table_saddr, uint32_t idx) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(table_saddr + (idx << 2)) : "memory");
+}
+
 // One warp, one family, one staged tile: the family's column offsets and strides sit in registers (NLO byte-lane
 // variables, NHI 16-bit-lane variables, both compile-time), each lane walks the tile 8 samples at a time.
 // NLO < 0 selects the generic (runtime trip count) body.
 template <int NLO, int NHI>
 __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ ent, int n_lo, int n_hi,
-                                                  const unsigned char* __restrict__ tile, uint32_t* __restrict__ tb,
+                                                  const unsigned char* __restrict__ tile, int w0, int w1, uint32_t* __restrict__ tb,
                                                   uint32_t nc, int lane) {
+  const uint32_t ts = smem_u32(tb);
   constexpr bool GENERIC = NLO < 0;
   constexpr int RLO = GENERIC ? 1 : (NLO > 0 ? NLO : 1), RHI = GENERIC ? 1 : (NHI > 0 ? NHI : 1);
   uint32_t off_lo[RLO], s_lo[RLO], off_hi[RHI], s_hi[RHI];
@@ -119,7 +124,7 @@ __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ e
     for (int k = 0; k < NHI; ++k) { off_hi[k] = ent[NLO + k] & 0xffffu; s_hi[k] = ent[NLO + k] >> 16; }
   }
 #pragma unroll 2
-  for (int wofs = lane * 8; wofs < TILE; wofs += 32 * 8) {
+  for (int wofs = w0 + lane * 8; wofs < w1; wofs += 32 * 8) {
     const unsigned char* st = tile + wofs;
     uint32_t a8x = 0, a8y = 0, aEx = 0, aOx = 0, aEy = 0, aOy = 0, any = 0;
     if (GENERIC) {
@@ -160,23 +165,23 @@ __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ e
       count_family_exact(ent, n_lo + n_hi, st, tb, nc);
     } else if ((!GENERIC && NHI == 0) || (GENERIC && n_hi == 0)) {
       // byte-lane only: the index is a byte and the table is padded to 256 cells -> no clamp needed
-      atomicAdd(tb + (a8x & 0xffu), 1u);
-      atomicAdd(tb + ((a8x >> 8) & 0xffu), 1u);
-      atomicAdd(tb + ((a8x >> 16) & 0xffu), 1u);
-      atomicAdd(tb + (a8x >> 24), 1u);
-      atomicAdd(tb + (a8y & 0xffu), 1u);
-      atomicAdd(tb + ((a8y >> 8) & 0xffu), 1u);
-      atomicAdd(tb + ((a8y >> 16) & 0xffu), 1u);
-      atomicAdd(tb + (a8y >> 24), 1u);
+      red_inc(ts, __byte_perm(a8x, 0, 0x4440));
+      red_inc(ts, __byte_perm(a8x, 0, 0x4441));
+      red_inc(ts, __byte_perm(a8x, 0, 0x4442));
+      red_inc(ts, __byte_perm(a8x, 0, 0x4443));
+      red_inc(ts, __byte_perm(a8y, 0, 0x4440));
+      red_inc(ts, __byte_perm(a8y, 0, 0x4441));
+      red_inc(ts, __byte_perm(a8y, 0, 0x4442));
+      red_inc(ts, __byte_perm(a8y, 0, 0x4443));
     } else {
-      atomicAdd(tb + min((a8x & 0xffu) + (aEx & 0xffffu), nc), 1u);      // cell nc is the family's spare
-      atomicAdd(tb + min(((a8x >> 8) & 0xffu) + (aOx & 0xffffu), nc), 1u);
-      atomicAdd(tb + min(((a8x >> 16) & 0xffu) + (aEx >> 16), nc), 1u);
-      atomicAdd(tb + min((a8x >> 24) + (aOx >> 16), nc), 1u);
-      atomicAdd(tb + min((a8y & 0xffu) + (aEy & 0xffffu), nc), 1u);
-      atomicAdd(tb + min(((a8y >> 8) & 0xffu) + (aOy & 0xffffu), nc), 1u);
-      atomicAdd(tb + min(((a8y >> 16) & 0xffu) + (aEy >> 16), nc), 1u);
-      atomicAdd(tb + min((a8y >> 24) + (aOy >> 16), nc), 1u);
+      red_inc(ts, min(__byte_perm(a8x, 0, 0x4440) + (aEx & 0xffffu), nc));      // cell nc is the family's spare
+      red_inc(ts, min(__byte_perm(a8x, 0, 0x4441) + (aOx & 0xffffu), nc));
+      red_inc(ts, min(__byte_perm(a8x, 0, 0x4442) + (aEx >> 16), nc));
+      red_inc(ts, min(__byte_perm(a8x, 0, 0x4443) + (aOx >> 16), nc));
+      red_inc(ts, min(__byte_perm(a8y, 0, 0x4440) + (aEy & 0xffffu), nc));
+      red_inc(ts, min(__byte_perm(a8y, 0, 0x4441) + (aOy & 0xffffu), nc));
+      red_inc(ts, min(__byte_perm(a8y, 0, 0x4442) + (aEy >> 16), nc));
+      red_inc(ts, min(__byte_perm(a8y, 0, 0x4443) + (aOy >> 16), nc));
     }
   }
 }
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
+  __shared__ int s_next[2];
   __shared__ __align__(8) uint64_t bar[2];
   const int g = blockIdx.x % n_groups;       // groups of one tile are neighbours in launch order (L2 reuse)
   const int64_t x = blockIdx.x / n_groups;
@@ -206,6 +212,7 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    s_next[0] = s_next[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -222,32 +229,44 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   int buf = 0;
   uint32_t phase0 = 0, phase1 = 0;
   if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int n_fams = G.n_fams;
+  // few families: split every family's tile into 2 or 4 parts so the 8 warps stay balanced
+  const int split_log2 = n_fams >= 32 ? 0 : (n_fams >= 12 ? 1 : 2);
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
     if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
     if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
     const unsigned char* tile = stage + size_t(buf) * tile_bytes;
-    // family-stationary: each warp takes whole families, so the per-family metadata is loop invariant
-    for (int f = warp; f < n_fams; f += COUNT_TPB / 32) {
+    // family-stationary: a warp takes (family, part of the tile) units, so the per-family metadata is loop invariant;
+    // units are handed out dynamically (families are sorted by cost, largest first)
+    const int n_units = n_fams << split_log2;
+    for (;;) {
+      int unit = 0;
+      if (lane == 0) unit = atomicAdd(&s_next[buf], 1);
+      unit = __shfl_sync(0xffffffffu, unit, 0);
+      if (unit >= n_units) break;
+      const int f = unit >> split_log2;
+      const int part = unit & ((1 << split_log2) - 1);
+      const int w0 = part * (TILE >> split_log2), w1 = w0 + (TILE >> split_log2);
       const uint4 hdr = s_hdr[f];        // x: table offset, y: n_cells, z: n_lo | n_hi << 8, w: first entry
       uint32_t* tb = tbl + hdr.x;
       const uint32_t nc = hdr.y;
       const int n_lo = hdr.z & 0xffu, n_hi = (hdr.z >> 8) & 0xffu;
       const uint32_t* ent = s_ent + hdr.w;
       switch (hdr.z) {
-#define CBN_CASE(LO, HI) case (LO) | ((HI) << 8): count_family_tile<LO, HI>(ent, n_lo, n_hi, tile, tb, nc, lane); break;
+#define CBN_CASE(LO, HI) case (LO) | ((HI) << 8): count_family_tile<LO, HI>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane); break;
         CBN_CASE(1, 0) CBN_CASE(2, 0) CBN_CASE(3, 0) CBN_CASE(4, 0) CBN_CASE(5, 0) CBN_CASE(6, 0)
         CBN_CASE(1, 1) CBN_CASE(2, 1) CBN_CASE(3, 1) CBN_CASE(4, 1)
         CBN_CASE(1, 2) CBN_CASE(2, 2) CBN_CASE(3, 2) CBN_CASE(4, 2)
         CBN_CASE(1, 3) CBN_CASE(2, 3) CBN_CASE(3, 3) CBN_CASE(4, 3)
 #undef CBN_CASE
-        default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, tb, nc, lane); break;
+        default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane); break;
       }
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
+    if (threadIdx.x == 0) s_next[buf] = 0;   // next use of this counter is two iterations (and one barrier) away
     buf ^= 1;
   }
   // flush the private tables into the caller's int64 tables
@@ -402,6 +421,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         gentries += fams[best].n_vars;
         used[best] = 1; --left;
       }
+      std::stable_sort(members.begin(), members.end(), [&](int a, int b2) { return fams[a].n_vars > fams[b2].n_vars; });
       groups.push_back(members);
       group_cols.emplace_back(cols.begin(), cols.end());
     }
