@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   const int lane = threadIdx.x & 31;
   const int n_fams = G.n_fams;
   // few families: split every family's tile into 2 or 4 parts so the 8 warps stay balanced
-  const int split_log2 = n_fams >= 32 ? 0 : (n_fams >= 12 ? 1 : 2);
+  const int split_log2 = n_fams >= 8 ? 0 : (n_fams >= 4 ? 1 : 2);
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
@@ -240,13 +240,9 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
     const unsigned char* tile = stage + size_t(buf) * tile_bytes;
     // family-stationary: a warp takes (family, part of the tile) units, so the per-family metadata is loop invariant;
-    // units are handed out dynamically (families are sorted by cost, largest first)
+    // units go round-robin over the warps (families are sorted by cost, largest first)
     const int n_units = n_fams << split_log2;
-    for (;;) {
-      int unit = 0;
-      if (lane == 0) unit = atomicAdd(&s_next[buf], 1);
-      unit = __shfl_sync(0xffffffffu, unit, 0);
-      if (unit >= n_units) break;
+    for (int unit = threadIdx.x >> 5; unit < n_units; unit += COUNT_TPB / 32) {
       const int f = unit >> split_log2;
       const int part = unit & ((1 << split_log2) - 1);
       const int w0 = part * (TILE >> split_log2), w1 = w0 + (TILE >> split_log2);
@@ -266,7 +262,6 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
       }
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
-    if (threadIdx.x == 0) s_next[buf] = 0;   // next use of this counter is two iterations (and one barrier) away
     buf ^= 1;
   }
   // flush the private tables into the caller's int64 tables
