@@ -64,6 +64,15 @@ struct DeviceGuard {
 
 static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// per-family descriptor of the counts -> probabilities kernel (fit.cu), also cached inside count plans
+struct CptFam {
+  long long off;
+  int n_rows;   // parent configurations
+  int card;     // node cardinality
+};
+int cbn_launch_cpt_kernel(cbn_ctx* ctx, const long long* counts, const CptFam* d_fams, int n_fams, int max_rows,
+                          long long n_total, float* joint, float* cond, cudaStream_t s);
+
 // validates one family descriptor; returns its table size
 static inline int check_family(cbn_ctx* ctx, const cbn_family* f, int n_cols, int64_t* n_cells_out) {
   if (f->n_vars < 1 || f->n_vars > CBN_MAX_FAMILY_VARS)

@@ -17,6 +17,8 @@
 //     clamped onto a spare cell per family that is never flushed.
 // count_direct_kernel is the same arithmetic straight from global memory: used for the tail
 // (n % 2048 samples) and, with global atomics, for families too large for shared memory.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 #include <set>
@@ -42,6 +44,22 @@ struct FamRec {          // direct kernel: 112 bytes, one per family
   int32_t reserved;
   int32_t var[CBN_MAX_FAMILY_VARS];
   int32_t stride[CBN_MAX_FAMILY_VARS];
+};
+
+// A super-family is the union scope of several families counted with ONE update per sample; the member tables are
+// its marginals (integer sums), produced when the CTA flushes.  A plain family is a super-family with one member.
+struct SuperInfo {
+  int32_t n_vars;
+  int32_t card[CBN_MAX_FAMILY_VARS];      // cards of the super-family's variables, in table order (last fastest)
+  int32_t m_start, m_count;               // members
+};
+struct SuperMember {
+  long long goff;                         // the member family's table in the caller's counts
+  int32_t n_vars;
+  int32_t n_cells;
+  int32_t pos[CBN_MAX_FAMILY_VARS];       // position of the member's k-th variable inside the super-family
+  int32_t stride[CBN_MAX_FAMILY_VARS];    // its stride inside the member's table
+  int32_t col[CBN_MAX_FAMILY_VARS];       // global column (exact path)
 };
 
 struct TileGroup {
@@ -79,6 +97,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// exact redo of a MERGED super-family for the 8 samples of a lane: a sample with an unseen code is skipped only for
+// the member families that contain that variable, so the members are updated one by one, straight in global memory
+__device__ __noinline__ void count_members_exact(const uint32_t* __restrict__ ent, const SuperInfo* __restrict__ info,
+                                                 const SuperMember* __restrict__ members, const unsigned char* st,
+                                                 unsigned long long* __restrict__ counts) {
+  const SuperInfo I = *info;
+  for (int q = 0; q < 8; ++q) {
+    int code[CBN_MAX_FAMILY_VARS];
+    // entry e holds the super-family's variable n_vars-1-e (the stream runs from the fastest axis backwards)
+    for (int e = 0; e < I.n_vars; ++e) code[I.n_vars - 1 - e] = st[(ent[e] & 0xffffu) + q];
+    for (int m = 0; m < I.m_count; ++m) {
+      const SuperMember& M = members[I.m_start + m];
+      uint32_t idx = 0;
+      bool ok = true;
+      for (int k = 0; k < M.n_vars; ++k) {
+        const int c = code[M.pos[k]];
+        ok &= (c != CBN_UNSEEN);
+        idx += uint32_t(c) * uint32_t(M.stride[k]);
+      }
+      if (ok && idx < uint32_t(M.n_cells)) atomicAdd(counts + M.goff + idx, 1ull);
+    }
+  }
+}
+
 // exact redo of one family for the 8 samples of a lane (a code >= 128 was seen: cardinality > 128 or CBN_UNSEEN)
 __device__ __noinline__ void count_family_exact(const uint32_t* __restrict__ ent, int n_ent, const unsigned char* st,
                                                 uint32_t* tb, uint32_t nc) {
@@ -112,7 +154,8 @@ __device__ __forceinline__ void red_inc(uint32_t table_saddr, uint32_t idx) {
 template <int NLO, int NHI>
 __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ ent, int n_lo, int n_hi,
                                                   const unsigned char* __restrict__ tile, int w0, int w1, uint32_t* __restrict__ tb,
-                                                  uint32_t nc, int lane) {
+                                                  uint32_t nc, int lane, const SuperInfo* __restrict__ info,
+                                                  const SuperMember* __restrict__ members, unsigned long long* __restrict__ counts) {
   const uint32_t ts = smem_u32(tb);
   constexpr bool GENERIC = NLO < 0;
   constexpr int RLO = GENERIC ? 1 : (NLO > 0 ? NLO : 1), RHI = GENERIC ? 1 : (NHI > 0 ? NHI : 1);
@@ -162,7 +205,8 @@ __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ e
       }
     }
     if (any & 0x80808080u) {
-      count_family_exact(ent, n_lo + n_hi, st, tb, nc);
+      if (info->m_count > 1) count_members_exact(ent, info, members, st, counts);
+      else count_family_exact(ent, n_lo + n_hi, st, tb, nc);
     } else if ((!GENERIC && NHI == 0) || (GENERIC && n_hi == 0)) {
       // byte-lane only: the index is a byte and the table is padded to 256 cells -> no clamp needed
       red_inc(ts, __byte_perm(a8x, 0, 0x4440));
@@ -190,7 +234,7 @@ __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ e
 __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
     const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint4* __restrict__ famhdr,
-    const long long* __restrict__ goff, unsigned long long* __restrict__ counts) {
+    const SuperInfo* __restrict__ sinfo, const SuperMember* __restrict__ members, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
   __shared__ int s_next[2];
@@ -251,28 +295,43 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
       const uint32_t nc = hdr.y;
       const int n_lo = hdr.z & 0xffu, n_hi = (hdr.z >> 8) & 0xffu;
       const uint32_t* ent = s_ent + hdr.w;
+      const SuperInfo* info = sinfo + G.fam_start + f;
       switch (hdr.z) {
-#define CBN_CASE(LO, HI) case (LO) | ((HI) << 8): count_family_tile<LO, HI>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane); break;
+#define CBN_CASE(LO, HI) case (LO) | ((HI) << 8): count_family_tile<LO, HI>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane, info, members, counts); break;
         CBN_CASE(1, 0) CBN_CASE(2, 0) CBN_CASE(3, 0) CBN_CASE(4, 0) CBN_CASE(5, 0) CBN_CASE(6, 0)
         CBN_CASE(1, 1) CBN_CASE(2, 1) CBN_CASE(3, 1) CBN_CASE(4, 1)
         CBN_CASE(1, 2) CBN_CASE(2, 2) CBN_CASE(3, 2) CBN_CASE(4, 2)
         CBN_CASE(1, 3) CBN_CASE(2, 3) CBN_CASE(3, 3) CBN_CASE(4, 3)
 #undef CBN_CASE
-        default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane); break;
+        default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane, info, members, counts); break;
       }
     }
     __syncthreads();   // every read of this buffer is done before it is refilled
     buf ^= 1;
   }
-  // flush the private tables into the caller's int64 tables
+  // flush: every non-zero cell of a (super-)family table is added to each member family's int64 table at the cell's
+  // marginal index (a plain family has one member with identical layout)
   for (int f = 0; f < n_fams; ++f) {
     const uint4 hdr = s_hdr[f];
     const int nc = int(hdr.y);
-    unsigned long long* dst = counts + goff[G.fam_start + f];
+    const SuperInfo I = sinfo[G.fam_start + f];
     const uint32_t* tb = tbl + hdr.x;
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const uint32_t v = tb[c];
-      if (v) atomicAdd(dst + c, (unsigned long long)v);
+      if (!v) continue;
+      if (I.m_count == 1) {
+        atomicAdd(counts + members[I.m_start].goff + c, (unsigned long long)v);
+        continue;
+      }
+      int coord[CBN_MAX_FAMILY_VARS];
+      int rem = c;
+      for (int j = I.n_vars - 1; j >= 0; --j) { coord[j] = rem % I.card[j]; rem /= I.card[j]; }
+      for (int m = 0; m < I.m_count; ++m) {
+        const SuperMember& M = members[I.m_start + m];
+        int idx = 0;
+        for (int k = 0; k < M.n_vars; ++k) idx += coord[M.pos[k]] * M.stride[k];
+        atomicAdd(counts + M.goff + idx, (unsigned long long)v);
+      }
     }
   }
 }
@@ -345,20 +404,26 @@ struct cbn_count_plan {
   int* d_gcols = nullptr;
   uint32_t* d_entries = nullptr;
   uint4* d_famhdr = nullptr;
+  SuperInfo* d_sinfo = nullptr;
+  SuperMember* d_members = nullptr;
+  int n_supers = 0;
   // direct kernel (tail + large families): small families grouped by the same clustering, large ones at the end
-  int n_small = 0, n_large = 0;
+  int n_small = 0, n_large = 0, n_direct_groups = 0;
   size_t direct_smem = 0;
   std::vector<int> group_start;
   FamRec* d_recs = nullptr;
   int* d_group_start = nullptr;
   long long* d_goff = nullptr;
+  // counts -> probabilities descriptors of ALL families (cbn_cpt_from_plan)
+  CptFam* d_cpt = nullptr;
+  int cpt_max_rows = 1;
 };
 
 extern "C" void cbn_count_plan_destroy(cbn_count_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_groups); cudaFree(p->d_gcols); cudaFree(p->d_entries); cudaFree(p->d_famhdr);
-  cudaFree(p->d_recs); cudaFree(p->d_group_start); cudaFree(p->d_goff);
+  cudaFree(p->d_groups); cudaFree(p->d_gcols); cudaFree(p->d_entries); cudaFree(p->d_famhdr); cudaFree(p->d_sinfo); cudaFree(p->d_members);
+  cudaFree(p->d_recs); cudaFree(p->d_group_start); cudaFree(p->d_goff); cudaFree(p->d_cpt);
   delete p;
 }
 
@@ -376,6 +441,10 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   if (!fams || n_fams < 1 || n_cols < 1 || !out)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_plan_create: bad argument");
   DeviceGuard dg(ctx->device);
+  // union-table limit of the super-family merge (cells); CBN_COUNT_MERGE_CELLS=0 disables merging
+  int64_t merge_cells = 4096;
+  if (const char* env = getenv("CBN_COUNT_MERGE_CELLS")) merge_cells = atoll(env);
+  merge_cells = std::min<int64_t>(merge_cells, MAX_GROUP_CELLS);
   std::vector<int64_t> cells(n_fams);
   std::vector<int> small, large;
   for (int f = 0; f < n_fams; ++f) {
@@ -383,40 +452,92 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     if (rc) return rc;
     (cells[f] <= MAX_GROUP_CELLS && fams[f].n_vars <= MAX_GCOLS ? small : large).push_back(f);
   }
-  // ---- cluster the small families by column overlap (fewer staged columns per group = less L2 traffic)
+  // ---- merge families into super-families: one shared-memory update per sample then serves several families.
+  // Greedy: grow a seed by the family that enlarges the union table the least while it stays <= MERGE_CELLS.
+  struct Super { std::vector<int> vars, cards, members; int64_t cells; };
+  std::vector<Super> supers;
+  {
+    auto mergeable = [&](int f) {
+      for (int j = 0; j < fams[f].n_vars; ++j) if (fams[f].card[j] > 128) return false;   // codes >= 128 always take the exact path
+      return true;
+    };
+    std::vector<int> order(small);
+    std::stable_sort(order.begin(), order.end(), [&](int a2, int b2) { return cells[a2] > cells[b2]; });
+    std::vector<char> used(n_fams, 0);
+    for (int seed : order) {
+      if (used[seed]) continue;
+      used[seed] = 1;
+      Super S;
+      S.members.push_back(seed);
+      std::vector<std::pair<int, int>> u;          // (var, card)
+      for (int j = 0; j < fams[seed].n_vars; ++j) u.emplace_back(fams[seed].var[j], fams[seed].card[j]);
+      int64_t ucells = cells[seed];
+      while (merge_cells > 0 && mergeable(seed)) {
+        int best = -1; int64_t best_cells = 0; int best_vars = 0;
+        for (int h : order) {
+          if (used[h] || !mergeable(h)) continue;
+          int64_t c = ucells; int extra = 0;
+          for (int j = 0; j < fams[h].n_vars; ++j) {
+            bool in = false;
+            for (auto& pr : u) if (pr.first == fams[h].var[j]) { in = true; break; }
+            if (!in) { c *= fams[h].card[j]; ++extra; }
+          }
+          if (extra == fams[h].n_vars && ucells > 1) continue;          // disjoint scopes: nothing to share
+          if (c > merge_cells || (int)u.size() + extra > CBN_MAX_FAMILY_VARS) continue;
+          if (best < 0 || c < best_cells || (c == best_cells && fams[h].n_vars > best_vars)) { best = h; best_cells = c; best_vars = fams[h].n_vars; }
+        }
+        if (best < 0) break;
+        used[best] = 1;
+        S.members.push_back(best);
+        for (int j = 0; j < fams[best].n_vars; ++j) {
+          bool in = false;
+          for (auto& pr : u) if (pr.first == fams[best].var[j]) { in = true; break; }
+          if (!in) u.emplace_back(fams[best].var[j], fams[best].card[j]);
+        }
+        ucells = best_cells;
+      }
+      // table order: largest cardinalities slowest, smallest fastest -> as many variables as possible in byte lanes
+      if (S.members.size() > 1) std::stable_sort(u.begin(), u.end(), [](const std::pair<int,int>& x, const std::pair<int,int>& y) { return x.second > y.second; });
+      for (auto& pr : u) { S.vars.push_back(pr.first); S.cards.push_back(pr.second); }
+      S.cells = ucells;
+      supers.push_back(S);
+    }
+  }
+  const int n_sup = (int)supers.size();
+  // ---- cluster the super-families by column overlap (fewer staged columns per group = less L2 traffic)
   std::vector<std::vector<int>> groups;
   std::vector<std::vector<int>> group_cols;
   {
-    std::vector<char> used(n_fams, 0);
-    size_t left = small.size();
-    size_t cursor = 0;
+    std::vector<char> used(n_sup, 0);
+    int left = n_sup;
+    int cursor = 0;
+    auto alloc_of = [&](int q) { return std::max<int64_t>(supers[q].cells + 1, 256); };   // shared-memory cells a table takes
     while (left > 0) {
-      while (used[small[cursor]]) ++cursor;
-      int seed = small[cursor];
+      while (used[cursor]) ++cursor;
+      int seed = cursor;
       std::vector<int> members{seed};
-      std::set<int> cols(fams[seed].var, fams[seed].var + fams[seed].n_vars);
-      auto alloc_of = [&](int f) { return std::max<int64_t>(cells[f] + 1, 256); };   // upper bound of the shared-memory cells a family takes
+      std::set<int> cols(supers[seed].vars.begin(), supers[seed].vars.end());
       int64_t gcells = alloc_of(seed);
-      int gentries = fams[seed].n_vars;
+      int gentries = (int)supers[seed].vars.size();
       used[seed] = 1; --left;
       while (left > 0 && (int)members.size() < MAX_GROUP_FAMS) {
         int best = -1, best_new = 1 << 30, best_shared = -1;
-        for (int f : small) {
-          if (used[f] || gcells + alloc_of(f) > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
-              gentries + fams[f].n_vars > MAX_GROUP_ENTRIES) continue;
+        for (int q = 0; q < n_sup; ++q) {
+          if (used[q] || gcells + alloc_of(q) > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
+              gentries + (int)supers[q].vars.size() > MAX_GROUP_ENTRIES) continue;
           int nnew = 0, shared = 0;
-          for (int j = 0; j < fams[f].n_vars; ++j) (cols.count(fams[f].var[j]) ? shared : nnew)++;
+          for (int v : supers[q].vars) (cols.count(v) ? shared : nnew)++;
           if ((int)cols.size() + nnew > MAX_GCOLS) continue;
-          if (nnew < best_new || (nnew == best_new && shared > best_shared)) { best = f; best_new = nnew; best_shared = shared; }
+          if (nnew < best_new || (nnew == best_new && shared > best_shared)) { best = q; best_new = nnew; best_shared = shared; }
         }
         if (best < 0) break;
         members.push_back(best);
-        for (int j = 0; j < fams[best].n_vars; ++j) cols.insert(fams[best].var[j]);
+        for (int v : supers[best].vars) cols.insert(v);
         gcells += alloc_of(best);
-        gentries += fams[best].n_vars;
+        gentries += (int)supers[best].vars.size();
         used[best] = 1; --left;
       }
-      std::stable_sort(members.begin(), members.end(), [&](int a, int b2) { return fams[a].n_vars > fams[b2].n_vars; });
+      std::stable_sort(members.begin(), members.end(), [&](int a2, int b2) { return supers[a2].vars.size() > supers[b2].vars.size(); });
       groups.push_back(members);
       group_cols.emplace_back(cols.begin(), cols.end());
     }
@@ -425,56 +546,92 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
   p->device = ctx->device; p->sm_count = ctx->sm_count; p->n_fams = n_fams; p->n_cols = n_cols;
   p->n_groups = (int)groups.size(); p->n_small = (int)small.size(); p->n_large = (int)large.size();
+  p->n_supers = n_sup;
 
   std::vector<TileGroup> h_groups;
   std::vector<int> h_gcols;
   std::vector<uint32_t> h_entries;
   std::vector<uint4> h_famhdr;
-  std::vector<long long> h_goff;       // shared by both kernels: record order = group order, then large families
-  std::vector<FamRec> h_recs;
-  std::vector<int> h_group_start{0};
-  size_t tile_smem = 0, direct_smem = 0;
+  std::vector<SuperInfo> h_sinfo;
+  std::vector<SuperMember> h_members;
+  size_t tile_smem = 0;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     TileGroup G{};
     G.fam_start = (int)h_famhdr.size(); G.n_fams = (int)groups[gi].size();
     G.col_start = (int)h_gcols.size(); G.n_cols = (int)group_cols[gi].size();
     G.ent_start = (int)h_entries.size();
-    int off = 0, off_direct = 0;
-    for (int f : groups[gi]) {
-      const cbn_family& F = fams[f];
-      FamRec fr{};
-      fr.smem_off = off_direct;
-      fr.n_cells = (int)cells[f];
-      fr.n_vars = F.n_vars;
-      // strides, node fastest; walk from the node backwards: byte lanes while the partial index stays < 256
+    int off = 0;
+    for (int q : groups[gi]) {
+      const Super& S = supers[q];
+      const int nv = (int)S.vars.size();
+      // strides, last variable fastest; walk backwards: byte lanes while the partial index stays < 256
       int64_t st = 1, reach = 0;
-      int n_lo = 0, n_hi = 0, fam_alloc = 0;
+      int n_lo = 0, n_hi = 0;
       const int ent_first = (int)h_entries.size() - G.ent_start;
-      for (int j = F.n_vars - 1; j >= 0; --j) {
-        fr.var[j] = F.var[j];
-        fr.stride[j] = (int32_t)st;
-        const int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), F.var[j]) - group_cols[gi].begin());
-        reach += int64_t(F.card[j] - 1) * st;
+      std::vector<int64_t> sstride(nv);
+      for (int j = nv - 1; j >= 0; --j) {
+        const int local = int(std::lower_bound(group_cols[gi].begin(), group_cols[gi].end(), S.vars[j]) - group_cols[gi].begin());
+        sstride[j] = st;
+        reach += int64_t(S.cards[j] - 1) * st;
         if (reach > 255 || n_hi > 0) ++n_hi; else ++n_lo;
         h_entries.push_back((uint32_t(st) << 16) | uint32_t(local * TILE));
-        st *= F.card[j];
+        st *= S.cards[j];
       }
-      h_famhdr.push_back(make_uint4(uint32_t(off), uint32_t(cells[f]), uint32_t(n_lo) | (uint32_t(n_hi) << 8), uint32_t(ent_first)));
-      fam_alloc = n_hi == 0 ? 256 : (int)cells[f] + 1;   // byte-lane families: any byte is in range; others: one spare cell
-      h_recs.push_back(fr);
-      h_goff.push_back(F.table_offset);
-      off += fam_alloc;
-      off_direct += (int)cells[f];
+      h_famhdr.push_back(make_uint4(uint32_t(off), uint32_t(S.cells), uint32_t(n_lo) | (uint32_t(n_hi) << 8), uint32_t(ent_first)));
+      off += n_hi == 0 ? 256 : (int)S.cells + 1;   // byte-lane tables: any byte is in range; others: one spare cell
+      SuperInfo I{};
+      I.n_vars = nv;
+      for (int j = 0; j < nv; ++j) I.card[j] = S.cards[j];
+      I.m_start = (int)h_members.size(); I.m_count = (int)S.members.size();
+      for (int f : S.members) {
+        const cbn_family& F = fams[f];
+        SuperMember M{};
+        M.goff = F.table_offset; M.n_vars = F.n_vars; M.n_cells = (int)cells[f];
+        int64_t ms = 1;
+        for (int k = F.n_vars - 1; k >= 0; --k) {
+          M.pos[k] = int(std::find(S.vars.begin(), S.vars.end(), F.var[k]) - S.vars.begin());
+          M.stride[k] = (int)ms;
+          M.col[k] = F.var[k];
+          ms *= F.card[k];
+        }
+        h_members.push_back(M);
+      }
+      h_sinfo.push_back(I);
     }
     G.n_entries = (int)h_entries.size() - G.ent_start;
     G.n_cells = off;
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
-    h_group_start.push_back((int)h_recs.size());
-    size_t s = ((((size_t(off) * 4 + 15) & ~size_t(15)) + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
-    tile_smem = std::max(tile_smem, s);
-    direct_smem = std::max(direct_smem, size_t(G.n_fams) * sizeof(FamRec) + size_t(off_direct) * 4);
+    size_t sm = ((((size_t(off) * 4 + 15) & ~size_t(15)) + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
+    tile_smem = std::max(tile_smem, sm);
   }
+  // ---- direct kernel (tail samples): the original small families, packed into shared-memory sized groups
+  std::vector<long long> h_goff;       // record order = direct groups, then large families
+  std::vector<FamRec> h_recs;
+  std::vector<int> h_group_start{0};
+  size_t direct_smem = 0;
+  {
+    int off_direct = 0, nf = 0;
+    auto close = [&]() {
+      if (nf == 0) return;
+      h_group_start.push_back((int)h_recs.size());
+      direct_smem = std::max(direct_smem, size_t(nf) * sizeof(FamRec) + size_t(off_direct) * 4);
+      off_direct = 0; nf = 0;
+    };
+    for (int f : small) {
+      if (off_direct + cells[f] > MAX_GROUP_CELLS || nf >= MAX_GROUP_FAMS) close();
+      const cbn_family& F = fams[f];
+      FamRec fr{};
+      fr.smem_off = off_direct; fr.n_cells = (int)cells[f]; fr.n_vars = F.n_vars;
+      int64_t st = 1;
+      for (int j = F.n_vars - 1; j >= 0; --j) { fr.var[j] = F.var[j]; fr.stride[j] = (int32_t)st; st *= F.card[j]; }
+      h_recs.push_back(fr);
+      h_goff.push_back(F.table_offset);
+      off_direct += (int)cells[f]; ++nf;
+    }
+    close();
+  }
+  p->n_direct_groups = (int)h_group_start.size() - 1;
   for (int f : large) {
     const cbn_family& F = fams[f];
     FamRec fr{};
@@ -491,9 +648,21 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   if (e == cudaSuccess) e = upload(&p->d_gcols, h_gcols);
   if (e == cudaSuccess) e = upload(&p->d_entries, h_entries);
   if (e == cudaSuccess) e = upload(&p->d_famhdr, h_famhdr);
+  if (e == cudaSuccess) e = upload(&p->d_sinfo, h_sinfo);
+  if (e == cudaSuccess) e = upload(&p->d_members, h_members);
   if (e == cudaSuccess) e = upload(&p->d_recs, h_recs);
   if (e == cudaSuccess) e = upload(&p->d_group_start, h_group_start);
   if (e == cudaSuccess) e = upload(&p->d_goff, h_goff);
+  {
+    std::vector<CptFam> h_cpt(n_fams);
+    for (int f = 0; f < n_fams; ++f) {
+      h_cpt[f].off = fams[f].table_offset;
+      h_cpt[f].card = fams[f].card[fams[f].n_vars - 1];
+      h_cpt[f].n_rows = (int)(cells[f] / h_cpt[f].card);
+      p->cpt_max_rows = std::max(p->cpt_max_rows, h_cpt[f].n_rows);
+    }
+    if (e == cudaSuccess) e = upload(&p->d_cpt, h_cpt);
+  }
   if (e == cudaSuccess && p->n_groups > 0) {
     e = cudaFuncSetAttribute(count_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
     int occ = 0;
@@ -511,6 +680,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
 }
 
 extern "C" int cbn_count_plan_groups(const cbn_count_plan* plan) { return plan ? plan->n_groups + (plan->n_large > 0) : 0; }
+extern "C" int cbn_count_plan_updates_per_sample(const cbn_count_plan* plan) { return plan ? plan->n_supers + plan->n_large : 0; }
 
 extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
                              unsigned long long* counts, cbn_stream stream) {
@@ -532,11 +702,11 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
       if (n_tiles > 0) {
         int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (plan->ctas_per_sm * plan->sm_count) / plan->n_groups));
         count_tiles_kernel<<<per_group * plan->n_groups, COUNT_TPB, plan->tile_smem, s>>>(
-            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_goff, counts);
+            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_sinfo, plan->d_members, counts);
         CBN_CHECK_LAUNCH(ctx);
       }
       if (tail > 0) {
-        dim3 grid((unsigned)((tail + COUNT_TPB - 1) / COUNT_TPB), plan->n_groups);
+        dim3 grid((unsigned)((tail + COUNT_TPB - 1) / COUNT_TPB), plan->n_direct_groups);
         count_direct_kernel<false><<<grid, COUNT_TPB, plan->direct_smem, s>>>(base + n_tiles * TILE, ld, tail, plan->d_recs,
                                                                                plan->d_group_start, 0, plan->d_goff, counts);
         CBN_CHECK_LAUNCH(ctx);
@@ -550,4 +720,12 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
     }
   }
   return CBN_OK;
+}
+
+extern "C" int cbn_cpt_from_plan(cbn_ctx* ctx, const cbn_count_plan* plan, const long long* counts, long long n_total,
+                                 float* joint, float* cond, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_cpt_from_plan: ctx is NULL");
+  if (!plan || !counts || n_total < 1 || (!joint && !cond)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_cpt_from_plan: bad argument");
+  DeviceGuard g(ctx->device);
+  return cbn_launch_cpt_kernel(ctx, counts, plan->d_cpt, plan->n_fams, plan->cpt_max_rows, n_total, joint, cond, (cudaStream_t)stream);
 }

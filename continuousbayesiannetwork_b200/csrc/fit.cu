@@ -242,12 +242,6 @@ extern "C" int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const f
 
 // =========================================================================== counts -> probabilities
 namespace {
-struct CptFam {
-  long long off;
-  int n_rows;   // parent configurations
-  int card;     // node cardinality
-};
-
 __global__ void __launch_bounds__(256) cpt_from_counts_kernel(const long long* __restrict__ counts,
                                                               const CptFam* __restrict__ fams, float n_total,
                                                               float* __restrict__ joint, float* __restrict__ cond) {
@@ -300,6 +294,17 @@ extern "C" int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const 
   }
   CBN_CHECK_LAUNCH(ctx);
   CBN_CUDA(ctx, cudaFreeAsync(d, s));
+  return CBN_OK;
+}
+
+int cbn_launch_cpt_kernel(cbn_ctx* ctx, const long long* counts, const CptFam* d_fams, int n_fams, int max_rows,
+                          long long n_total, float* joint, float* cond, cudaStream_t s) {
+  for (int f0 = 0; f0 < n_fams; f0 += 65535) {
+    int nf = std::min(65535, n_fams - f0);
+    dim3 grid(std::min((max_rows + 255) / 256, 1024), nf);
+    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d_fams + f0, (float)n_total, joint, cond);
+  }
+  CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
 }
 

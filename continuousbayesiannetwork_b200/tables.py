@@ -145,14 +145,21 @@ class DiscreteTables:
         assert codes.dtype == torch.uint8 and codes.dim() == 2 and codes.shape[0] == len(self.names)
         assert codes.stride(1) == 1
         lib = N.lib()
-        if self._count_plan is None:
-            h = C.c_void_p()
-            N.check(lib.cbn_count_plan_create(self.ctx.handle, self.fams, len(self.names), len(self.names), C.byref(h)),
-                    self.ctx.handle)
-            self._count_plan = h
+        self._ensure_plan()
         N.check(lib.cbn_count_run(self.ctx.handle, self._count_plan, codes.data_ptr(), codes.stride(0), int(n),
                                   self.counts.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
         self.n_total += int(n)
+
+    def _ensure_plan(self):
+        if self._count_plan is None:
+            h = C.c_void_p()
+            N.check(N.lib().cbn_count_plan_create(self.ctx.handle, self.fams, len(self.names), len(self.names), C.byref(h)),
+                    self.ctx.handle)
+            self._count_plan = h
+
+    def count_updates_per_sample(self) -> int:
+        self._ensure_plan()
+        return N.lib().cbn_count_plan_updates_per_sample(self._count_plan)
 
     def count_groups(self) -> int:
         return N.lib().cbn_count_plan_groups(self._count_plan) if self._count_plan is not None else 0
@@ -161,11 +168,13 @@ class DiscreteTables:
         """counts -> joint (fp32(c)/fp32(n)) and cond (joint / (parent + 1e-10))."""
         if self.n_total < 1:
             raise ValueError("no samples counted")
-        self.joint = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
-        self.cond = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
-        N.check(N.lib().cbn_cpt_from_counts(self.ctx.handle, self.counts.data_ptr(), self.fams, len(self.names),
-                                            self.n_total, self.joint.data_ptr(), self.cond.data_ptr(),
-                                            N.stream_ptr(self.device)), self.ctx.handle)
+        if self.joint is None or self.cond is None:
+            self.joint = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
+            self.cond = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
+        self._ensure_plan()
+        N.check(N.lib().cbn_cpt_from_plan(self.ctx.handle, self._count_plan, self.counts.data_ptr(), self.n_total,
+                                          self.joint.data_ptr(), self.cond.data_ptr(), N.stream_ptr(self.device)),
+                self.ctx.handle)
 
     def set_cond_tables(self, cpts: Sequence):
         """Install ground-truth conditional tables (synthetic workloads; no counting)."""

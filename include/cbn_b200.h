@@ -111,6 +111,8 @@ CBN_API int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_
                   unsigned long long* counts, cbn_stream stream);
 /* introspection for the bench: number of family groups (kernel passes over the tile) */
 CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
+/* table updates per sample after merging families that share variables into super-families (<= number of families) */
+CBN_API int cbn_count_plan_updates_per_sample(const cbn_count_plan* plan);
 
 /* ---- tables -> probabilities --------------------------------------------------------
  * joint[cell] = fp32(count) / fp32(n_total)                     (brute_force.py:43)
@@ -118,6 +120,10 @@ CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
  * Either output may be NULL.  IEEE fp32 division; unseen parent rows give zeros. */
 CBN_API int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const cbn_family* fams, int32_t n_fams,
                         long long n_total, float* joint, float* cond, cbn_stream stream);
+
+/* same, with the family descriptors cached inside a count plan: a pure kernel launch (no allocation, no copy) */
+CBN_API int cbn_cpt_from_plan(cbn_ctx* ctx, const cbn_count_plan* plan, const long long* counts, long long n_total,
+                      float* joint, float* cond, cbn_stream stream);
 
 /* The reference's sparse `mle_tensor` (brute_force.py:45-53) of ONE family: rows
  * [pa_1..pa_P, x, prob] for the non-zero cells, in lexicographic order.

@@ -84,7 +84,7 @@ def count():
 
         us = timeit(f, 3 if short else 10, 2)
         b = n * spec.n
-        print(f"count  {name:9s} n={n:>10d} vars={spec.n:4d} groups={t.count_groups():3d}  {us:10.1f} us  {n / us / 1e3:8.2f} G samples/s  {b / us / 1e3:8.1f} GB/s  {b / us / 1e3 / PEAK:6.3f} of peak")
+        print(f"count  {name:9s} n={n:>10d} vars={spec.n:4d} groups={t.count_groups():3d} upd/sample={t.count_updates_per_sample():3d}  {us:10.1f} us  {n / us / 1e3:8.2f} G samples/s  {b / us / 1e3:8.1f} GB/s  {b / us / 1e3 / PEAK:6.3f} of peak")
 
 
 if __name__ == "__main__":
