@@ -52,11 +52,14 @@ struct SuperInfo {
   int32_t n_vars;
   int32_t card[CBN_MAX_FAMILY_VARS];      // cards of the super-family's variables, in table order (last fastest)
   int32_t m_start, m_count;               // members
+  int32_t scratch_total;                  // sum of the members' table sizes (flush scratch)
 };
 struct SuperMember {
   long long goff;                         // the member family's table in the caller's counts
   int32_t n_vars;
   int32_t n_cells;
+  int32_t scratch_off;                    // the member's table inside the flush scratch
+  int32_t pad;
   int32_t pos[CBN_MAX_FAMILY_VARS];       // position of the member's k-th variable inside the super-family
   int32_t stride[CBN_MAX_FAMILY_VARS];    // its stride inside the member's table
   int32_t col[CBN_MAX_FAMILY_VARS];       // global column (exact path)
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   const int lane = threadIdx.x & 31;
   const int n_fams = G.n_fams;
   // few families: split every family's tile into 2 or 4 parts so the 8 warps stay balanced
-  const int split_log2 = n_fams >= 8 ? 0 : (n_fams >= 4 ? 1 : 2);
+  const int split_log2 = n_fams >= 16 ? 0 : (n_fams >= 8 ? 1 : (n_fams >= 4 ? 2 : 3));
   for (; t < n_tiles; t += xstride) {
     const int64_t tn = t + xstride;
     // the other buffer was released by the __syncthreads that closed the previous iteration
@@ -310,19 +313,31 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
     buf ^= 1;
   }
   // flush: every non-zero cell of a (super-)family table is added to each member family's int64 table at the cell's
-  // marginal index (a plain family has one member with identical layout)
+  // marginal index (a plain family has one member with identical layout).  Merged tables are first marginalised into
+  // shared memory (the staging buffers are free now), so the global atomics are one per member cell, not per super cell.
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
+  const int scratch_cap = int(2 * tile_bytes / 4);
   for (int f = 0; f < n_fams; ++f) {
     const uint4 hdr = s_hdr[f];
     const int nc = int(hdr.y);
     const SuperInfo I = sinfo[G.fam_start + f];
     const uint32_t* tb = tbl + hdr.x;
+    if (I.m_count == 1) {
+      unsigned long long* dst = counts + members[I.m_start].goff;
+      for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        const uint32_t v = tb[c];
+        if (v) atomicAdd(dst + c, (unsigned long long)v);
+      }
+      continue;
+    }
+    const bool in_smem = I.scratch_total <= scratch_cap;
+    if (in_smem) {
+      for (int i = threadIdx.x; i < I.scratch_total; i += blockDim.x) scratch[i] = 0u;
+      __syncthreads();
+    }
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const uint32_t v = tb[c];
       if (!v) continue;
-      if (I.m_count == 1) {
-        atomicAdd(counts + members[I.m_start].goff + c, (unsigned long long)v);
-        continue;
-      }
       int coord[CBN_MAX_FAMILY_VARS];
       int rem = c;
       for (int j = I.n_vars - 1; j >= 0; --j) { coord[j] = rem % I.card[j]; rem /= I.card[j]; }
@@ -330,8 +345,20 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
         const SuperMember& M = members[I.m_start + m];
         int idx = 0;
         for (int k = 0; k < M.n_vars; ++k) idx += coord[M.pos[k]] * M.stride[k];
-        atomicAdd(counts + M.goff + idx, (unsigned long long)v);
+        if (in_smem) atomicAdd(scratch + M.scratch_off + idx, v);
+        else atomicAdd(counts + M.goff + idx, (unsigned long long)v);
       }
+    }
+    if (in_smem) {
+      __syncthreads();
+      for (int m = 0; m < I.m_count; ++m) {
+        const SuperMember& M = members[I.m_start + m];
+        for (int c = threadIdx.x; c < M.n_cells; c += blockDim.x) {
+          const uint32_t v = scratch[M.scratch_off + c];
+          if (v) atomicAdd(counts + M.goff + c, (unsigned long long)v);
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -442,7 +469,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_plan_create: bad argument");
   DeviceGuard dg(ctx->device);
   // union-table limit of the super-family merge (cells); CBN_COUNT_MERGE_CELLS=0 disables merging
-  int64_t merge_cells = 4096;
+  int64_t merge_cells = 256;   // byte-lane tables: cheapest index arithmetic, cheapest flush (measured best on B200)
   if (const char* env = getenv("CBN_COUNT_MERGE_CELLS")) merge_cells = atoll(env);
   merge_cells = std::min<int64_t>(merge_cells, MAX_GROUP_CELLS);
   std::vector<int64_t> cells(n_fams);
@@ -583,10 +610,13 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       I.n_vars = nv;
       for (int j = 0; j < nv; ++j) I.card[j] = S.cards[j];
       I.m_start = (int)h_members.size(); I.m_count = (int)S.members.size();
+      int scratch_off = 0;
       for (int f : S.members) {
         const cbn_family& F = fams[f];
         SuperMember M{};
         M.goff = F.table_offset; M.n_vars = F.n_vars; M.n_cells = (int)cells[f];
+        M.scratch_off = scratch_off;
+        scratch_off += (int)cells[f];
         int64_t ms = 1;
         for (int k = F.n_vars - 1; k >= 0; --k) {
           M.pos[k] = int(std::find(S.vars.begin(), S.vars.end(), F.var[k]) - S.vars.begin());
@@ -596,6 +626,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         }
         h_members.push_back(M);
       }
+      I.scratch_total = scratch_off;
       h_sinfo.push_back(I);
     }
     G.n_entries = (int)h_entries.size() - G.ent_start;
