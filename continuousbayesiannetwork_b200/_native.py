@@ -118,6 +118,7 @@ SIGNATURES = {
     "cbn_ve_run_codes": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "cbn_ve_run_f32": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.c_int64, _P, _P]),
     "cbn_ve_run_codes_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "cbn_ve_run_codes_host_multi": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "cbn_batch_max": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "cbn_scale_by_inv": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "cbn_sample_forward": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(Family), _P, C.c_uint64,

@@ -1037,24 +1037,34 @@ static int ensure_io(cbn_ctx* ctx, size_t in_bytes, size_t out_bytes) {
   return CBN_OK;
 }
 
-extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
-                                     int64_t n_rows, float* posterior_host) {
+extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                           int64_t n_rows, float* const* posteriors_host) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
-  if (!plan || !posterior_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
+  if (!plan || !posteriors_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
-  if (plan->n_out != 1 || plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: fused and per-row plans are device-side only");
+  if (plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: per-row plans are device-side only");
+  const int n_out = plan->n_out, ct = plan->card_t;
+  for (int o = 0; o < n_out; ++o)
+    if (!posteriors_host[o]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: posterior %d is NULL", o);
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
   const int64_t chunk = 1 << 20;  // rows per chunk
   const int ne = std::max(plan->n_evidence, 1);
-  int rc = ensure_io(ctx, size_t(chunk) * ne, size_t(chunk) * plan->card_t * sizeof(float));
+  const size_t out_stride = size_t(chunk) * ct;   // floats per output inside a staging buffer
+  int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float));
   if (rc) return rc;
-  // Pageable or pinned caller memory: cudaMemcpyAsync handles both; pinned callers get true overlap.
+  // Pageable or pinned caller memory: pinned callers get direct DMA, pageable ones go through pinned staging.
   cudaPointerAttributes attr{};
   bool in_pinned = cudaPointerGetAttributes(&attr, ev_codes_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  bool out_pinned = cudaPointerGetAttributes(&attr, posterior_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  bool out_pinned = true;
+  for (int o = 0; o < n_out; ++o)
+    out_pinned = out_pinned && cudaPointerGetAttributes(&attr, posteriors_host[o]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   int64_t pending_row[2] = {-1, -1}, pending_m[2] = {0, 0};
+  auto drain = [&](int b) {
+    for (int o = 0; o < n_out; ++o)
+      memcpy(posteriors_host[o] + pending_row[b] * ct, (float*)ctx->io_pin_out[b] + o * out_stride, size_t(pending_m[b]) * ct * sizeof(float));
+  };
   int b = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, b ^= 1) {
     const int64_t m = std::min(chunk, n_rows - r0);
@@ -1062,8 +1072,7 @@ extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, cons
     // buffer b is free once its previous D2H has been consumed
     if (pending_row[b] >= 0) {
       CBN_CUDA(ctx, cudaStreamSynchronize(s));
-      if (!out_pinned)
-        memcpy(posterior_host + pending_row[b] * plan->card_t, ctx->io_pin_out[b], size_t(pending_m[b]) * plan->card_t * sizeof(float));
+      if (!out_pinned) drain(b);
       pending_row[b] = -1;
     }
     uint8_t* din = (uint8_t*)ctx->io_dev_in[b];
@@ -1078,22 +1087,30 @@ extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, cons
     if (!in_pinned && plan->n_evidence > 0)
       CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], size_t(chunk) * plan->n_evidence, cudaMemcpyHostToDevice, s));
     GatherOuts go{};
-    go.out[0] = (float*)ctx->io_dev_out[b];
+    for (int o = 0; o < n_out; ++o) go.out[o] = (float*)ctx->io_dev_out[b] + o * out_stride;
     go.normalize_mask = plan->normalize_mask;
     rc = ve_run_codes_impl(ctx, plan, din, chunk, m, go, s);
     if (rc) return rc;
-    float* dst = out_pinned ? posterior_host + r0 * plan->card_t : (float*)ctx->io_pin_out[b];
-    CBN_CUDA(ctx, cudaMemcpyAsync(dst, ctx->io_dev_out[b], size_t(m) * plan->card_t * sizeof(float), cudaMemcpyDeviceToHost, s));
+    for (int o = 0; o < n_out; ++o) {
+      float* dst = out_pinned ? posteriors_host[o] + r0 * ct : (float*)ctx->io_pin_out[b] + o * out_stride;
+      CBN_CUDA(ctx, cudaMemcpyAsync(dst, go.out[o], size_t(m) * ct * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
     pending_row[b] = r0; pending_m[b] = m;
   }
   for (int i = 0; i < 2; ++i) {
     if (pending_row[i] >= 0) {
       CBN_CUDA(ctx, cudaStreamSynchronize(ctx->io_stream[i]));
-      if (!out_pinned)
-        memcpy(posterior_host + pending_row[i] * plan->card_t, ctx->io_pin_out[i], size_t(pending_m[i]) * plan->card_t * sizeof(float));
+      if (!out_pinned) drain(i);
     }
   }
   return CBN_OK;
+}
+
+extern "C" int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                     int64_t n_rows, float* posterior_host) {
+  if (plan && plan->n_out != 1)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: fused plan with %d outputs; use cbn_ve_run_codes_host_multi", plan->n_out);
+  return cbn_ve_run_codes_host_multi(ctx, plan, ev_codes_host, ld, n_rows, &posterior_host);
 }
 
 // =========================================================================== reference scaling

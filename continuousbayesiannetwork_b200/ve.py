@@ -172,6 +172,18 @@ class FusedPlan:
         return list(outs)
 
 
+def _fused_run_codes_host(self, ev_codes_host: torch.Tensor, n_rows: int, outs_host: Sequence[torch.Tensor]):
+    """Host buffers in, host buffers out, one fused launch per chunk (copies inside; synchronous)."""
+    assert not ev_codes_host.is_cuda and len(outs_host) == self.n_out and all(not o.is_cuda for o in outs_host)
+    ptrs = N.ptr_array([o.data_ptr() for o in outs_host])
+    N.check(N.lib().cbn_ve_run_codes_host_multi(self.ctx.handle, self.handle, ev_codes_host.data_ptr(), ev_codes_host.stride(0),
+                                                int(n_rows), ptrs), self.ctx.handle)
+    return list(outs_host)
+
+
+FusedPlan.run_codes_host = _fused_run_codes_host
+
+
 class RowPlan:
     """A query whose evidence boundary is too large to tabulate: static tables for what could be eliminated at
     compile time + a per-row schedule of product / sum-out steps (``cbn_ve_plan_create_rows``)."""

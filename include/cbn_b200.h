@@ -235,6 +235,10 @@ CBN_API int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* c
 CBN_API int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
                           int64_t n_rows, float* posterior_host);
 
+/* fused plan, host buffers: posteriors_host = host array of cbn_ve_plan_outputs(plan) host pointers */
+CBN_API int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                int64_t n_rows, float* const* posteriors_host);
+
 /* reference scaling: BayesianNetwork.infer divides the whole batch by ONE global max
  * (bayesian_network.py:296).  max_out: device float (caller zero-initialises). */
 CBN_API int cbn_batch_max(cbn_ctx* ctx, const float* x, int64_t n, float* max_out, cbn_stream stream);

@@ -205,6 +205,8 @@ def test_fused_multi_target_launch_matches_single_plans():
             single = infer.plan(t, ev_names).run_codes(m, n)
             assert torch.equal(single, o), t
             assert bool((o[7] == 0).all())
+        host = fused.run_codes_host(m.cpu(), n, [torch.empty((n, 2), dtype=torch.float32) for _ in targets])
+        assert all(torch.equal(h, o.cpu()) for h, o in zip(host, outs))
     # mixed target cardinalities cannot be fused
     spec = synth.alarm()
     _, infer = install_cpts(spec, DEV)
