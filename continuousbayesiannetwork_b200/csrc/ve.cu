@@ -274,6 +274,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       uint32_t any = 0;
       if (mode == 0) {
         uint32_t acc = 0;
+#pragma unroll 4
         for (int j = 0; j < ne; ++j) {
           const uint32_t w = L.load4(T.slot[j], quad);
           any |= w;
@@ -282,6 +283,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
         i0 = acc & 0xffu; i1 = (acc >> 8) & 0xffu; i2 = (acc >> 16) & 0xffu; i3 = acc >> 24;
       } else if (mode == 1) {
         uint32_t accE = 0, accO = 0;
+#pragma unroll 4
         for (int j = 0; j < ne; ++j) {
           const uint32_t w = L.load4(T.slot[j], quad);
           const uint32_t s = (uint32_t)T.stride[j];
@@ -292,6 +294,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
         i0 = accE & 0xffffu; i1 = accO & 0xffffu; i2 = accE >> 16; i3 = accO >> 16;
       } else {
         i0 = i1 = i2 = i3 = 0;
+#pragma unroll 4
         for (int j = 0; j < ne; ++j) {
           const uint32_t w = L.load4(T.slot[j], quad);
           const uint32_t s = (uint32_t)T.stride[j];
@@ -347,6 +350,7 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
   const int ne = T.n_ev;
   if (mode == 0) {
     uint32_t acc = 0;
+#pragma unroll 4
     for (int j = 0; j < ne; ++j) {
       const uint32_t w = L.load4(T.slot[j], quad);
       any |= w;
@@ -355,6 +359,7 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
     i0 = acc & 0xffu; i1 = (acc >> 8) & 0xffu; i2 = (acc >> 16) & 0xffu; i3 = acc >> 24;
   } else if (mode == 1) {
     uint32_t accE = 0, accO = 0;
+#pragma unroll 4
     for (int j = 0; j < ne; ++j) {
       const uint32_t w = L.load4(T.slot[j], quad);
       const uint32_t s = (uint32_t)T.stride[j];
@@ -364,6 +369,7 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
     }
     i0 = accE & 0xffffu; i1 = accO & 0xffffu; i2 = accE >> 16; i3 = accO >> 16;
   } else {
+#pragma unroll 4
     for (int j = 0; j < ne; ++j) {
       const uint32_t w = L.load4(T.slot[j], quad);
       const uint32_t s = (uint32_t)T.stride[j];
@@ -654,8 +660,13 @@ int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     attr_set[ctx->device & 63] = true;
   }
   // one wave: as many CTAs as fit (register / shared-memory bound), the rest of the rows by the grid-stride loop
-  int per_sm = gather_min_blocks(CT);
-  if (p->blob_bytes > 0) per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm, (200 * 1024) / (p->blob_bytes + 1024)));
+  static size_t occ_smem = ~size_t(0);
+  static int occ = 1;
+  if (occ_smem != p->blob_bytes) {   // resident CTAs per SM for this shared-memory size (queried once)
+    CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_codes_kernel<CT>, GATHER_TPB, p->blob_bytes));
+    occ_smem = p->blob_bytes;
+  }
+  const int per_sm = std::max(occ, 1);
   gather_codes_kernel<CT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
       p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
@@ -685,7 +696,13 @@ int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_inter_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (p->blob_bytes + 1024)));
+  static size_t occ_smem = ~size_t(0);
+  static int occ = 1;
+  if (occ_smem != p->blob_bytes) {   // resident CTAs per SM for this shared-memory size (queried once)
+    CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_inter_kernel<CT, NOUT>, GATHER_TPB, p->blob_bytes));
+    occ_smem = p->blob_bytes;
+  }
+  const int per_sm = std::max(occ, 1);
   gather_inter_kernel<CT, NOUT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
       p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, outs);
   CBN_CHECK_LAUNCH(ctx);
