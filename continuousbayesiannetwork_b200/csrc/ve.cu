@@ -272,11 +272,13 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       const int mode = flags >> GT_MODE_SHIFT;
       const int ne = T.n_ev;
       uint32_t any = 0;
+      // rows past n_rows in the last quad hold whatever the buffer holds: force their codes to 0
+      const uint32_t tm = ((quad << 2) + 4 <= n_rows) ? 0xffffffffu : ((1u << (8 * int(n_rows - (quad << 2)))) - 1u);
       if (mode == 0) {
         uint32_t acc = 0;
 #pragma unroll 4
         for (int j = 0; j < ne; ++j) {
-          const uint32_t w = L.load4(T.slot[j], quad);
+          const uint32_t w = L.load4(T.slot[j], quad) & tm;
           any |= w;
           acc += w * (uint32_t)T.stride[j];            // 4 x 8-bit lanes
         }
@@ -285,7 +287,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
         uint32_t accE = 0, accO = 0;
 #pragma unroll 4
         for (int j = 0; j < ne; ++j) {
-          const uint32_t w = L.load4(T.slot[j], quad);
+          const uint32_t w = L.load4(T.slot[j], quad) & tm;
           const uint32_t s = (uint32_t)T.stride[j];
           any |= w;
           accE += (w & 0x00ff00ffu) * s;               // rows 0, 2 in 16-bit lanes
@@ -296,17 +298,21 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
         i0 = i1 = i2 = i3 = 0;
 #pragma unroll 4
         for (int j = 0; j < ne; ++j) {
-          const uint32_t w = L.load4(T.slot[j], quad);
+          const uint32_t w = L.load4(T.slot[j], quad) & tm;
           const uint32_t s = (uint32_t)T.stride[j];
           any |= w;
           i0 += (w & 0xffu) * s; i1 += ((w >> 8) & 0xffu) * s; i2 += ((w >> 16) & 0xffu) * s; i3 += (w >> 24) * s;
         }
       }
       ibad = 0;
+      const uint32_t lim = (uint32_t)T.n_cells - ((flags & GT_HAS_TARGET) ? CT : 1);
       if (any & 0x80808080u) {    // a code >= 128: cardinality > 128 or CBN_UNSEEN -- the packed lanes may have carried
-        const uint4 e = exact_index4(T, L, quad, (uint32_t)T.n_cells - ((flags & GT_HAS_TARGET) ? CT : 1), &ibad);
+        const uint4 e = exact_index4(T, L, quad, lim, &ibad);
         i0 = e.x; i1 = e.y; i2 = e.z; i3 = e.w;
+        ibad &= tm == 0xffffffffu ? 0xfu : ((1u << int(n_rows - (quad << 2))) - 1u);
       }
+      // an invalid code (>= cardinality) must never read outside the table
+      i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
     }
     bad |= ibad;
     const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
@@ -348,11 +354,13 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, any = 0, bad = 0;
   const int mode = T.flags >> GT_MODE_SHIFT;
   const int ne = T.n_ev;
+  // rows past n_rows in the last quad hold whatever the buffer holds: force their codes to 0
+  const uint32_t tm = ((quad << 2) + 4 <= n_rows) ? 0xffffffffu : ((1u << (8 * int(n_rows - (quad << 2)))) - 1u);
   if (mode == 0) {
     uint32_t acc = 0;
 #pragma unroll 4
     for (int j = 0; j < ne; ++j) {
-      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t w = L.load4(T.slot[j], quad) & tm;
       any |= w;
       acc += w * (uint32_t)T.stride[j];
     }
@@ -361,7 +369,7 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
     uint32_t accE = 0, accO = 0;
 #pragma unroll 4
     for (int j = 0; j < ne; ++j) {
-      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t w = L.load4(T.slot[j], quad) & tm;
       const uint32_t s = (uint32_t)T.stride[j];
       any |= w;
       accE += (w & 0x00ff00ffu) * s;
@@ -371,16 +379,20 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
   } else {
 #pragma unroll 4
     for (int j = 0; j < ne; ++j) {
-      const uint32_t w = L.load4(T.slot[j], quad);
+      const uint32_t w = L.load4(T.slot[j], quad) & tm;
       const uint32_t s = (uint32_t)T.stride[j];
       any |= w;
       i0 += (w & 0xffu) * s; i1 += ((w >> 8) & 0xffu) * s; i2 += ((w >> 16) & 0xffu) * s; i3 += (w >> 24) * s;
     }
   }
+  const uint32_t lim = (uint32_t)T.n_cells - W;
   if (any & 0x80808080u) {
-    const uint4 e = exact_index4(T, L, quad, (uint32_t)T.n_cells - W, &bad);
+    const uint4 e = exact_index4(T, L, quad, lim, &bad);
     i0 = e.x; i1 = e.y; i2 = e.z; i3 = e.w;
+    bad &= tm == 0xffffffffu ? 0xfu : ((1u << int(n_rows - (quad << 2))) - 1u);
   }
+  // an invalid code (>= cardinality) must never read outside the table
+  i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
   const uint32_t idx[4] = {i0, i1, i2, i3};
   float v[4][W];
 #pragma unroll
