@@ -2,6 +2,7 @@
 // per-row gather/product/normalise executor.  Fills the reference's empty inference plugin
 // slot (cbn/base/inference.py:7-23, cbn/inference/exact.py:13-14) and replaces the
 // mean-and-product loop of BayesianNetwork.infer (cbn/base/bayesian_network.py:243-296).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -188,9 +189,23 @@ __device__ __forceinline__ void load_slice(const float* __restrict__ src, float 
   }
 }
 
+// slice of a table that lives in global memory (L2): random rows, so no L1 allocation; a 32-byte slice is one
+// 256-bit load = exactly one sector per row (the table base must be 32-byte aligned)
+template <int CT>
+__device__ __forceinline__ void load_slice_l2(const float* __restrict__ src, float (&v)[CT]) {
+  if constexpr (CT == 8) {
+    ld_na_f256(src, v);
+  } else if constexpr (CT == 4) {
+    const float4 a = ld_nc_f128(reinterpret_cast<const float4*>(src));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+    load_slice<CT>(src, v);
+  }
+}
+
 template <int CT>
 __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad,
-                                             int64_t n_rows, float* __restrict__ out) {
+                                             int64_t n_rows, float* __restrict__ out, uint64_t st_pol = 0) {
   if (normalize) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -216,8 +231,13 @@ __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bo
     // 32-byte aligned (even CT; the host checks the base pointer), else 128-bit stores
     const float* flat = &p[0][0];
     if ((CT % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+      if (st_pol) {
 #pragma unroll
-      for (int v = 0; v < CT / 2; ++v) st_f256(dst + 8 * v, flat + 8 * v);
+        for (int v = 0; v < CT / 2; ++v) st_f256_hint(dst + 8 * v, flat + 8 * v, st_pol);
+      } else {
+#pragma unroll
+        for (int v = 0; v < CT / 2; ++v) st_f256(dst + 8 * v, flat + 8 * v);
+      }
     } else {
 #pragma unroll
       for (int v = 0; v < CT; ++v)
@@ -251,7 +271,8 @@ __device__ __noinline__ uint4 exact_index4(const GTable& T, const Loader& L, int
 // The four row indices are computed with SIMD-within-a-register arithmetic when the table is small enough.
 template <int CT, typename Loader>
 __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ pool,
-                                             const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs) {
+                                             const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs,
+                                             uint64_t st_pol = 0) {
   float p[4][CT];
   uint32_t bad = 0, ibad = 0;
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
@@ -260,7 +281,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
     const GTable& T = st[k];
     const int flags = T.flags;
     if (T.out_id != cur) {
-      if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
+      if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur], st_pol);
       cur = T.out_id;
       bad = 0;
 #pragma unroll
@@ -334,7 +355,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       }
     }
   }
-  if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur]);
+  if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur], st_pol);
 }
 
 // one straight 128-bit copy of the plan blob (descriptors + staged tables) into shared memory
@@ -349,7 +370,8 @@ __device__ __forceinline__ void stage_blob(const unsigned char* __restrict__ blo
 // computation and ONE contiguous slice (a single 32-byte sector for 4 binary targets) per row serve every target.
 template <int CT, int NOUT, typename Loader>
 __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float* __restrict__ base, const Loader& L,
-                                                   int64_t quad, int64_t n_rows, const GatherOuts& outs) {
+                                                   int64_t quad, int64_t n_rows, const GatherOuts& outs, uint64_t st_pol = 0,
+                                                   uint64_t ld_pol = 0) {
   constexpr int W = CT * NOUT;
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, any = 0, bad = 0;
   const int mode = T.flags >> GT_MODE_SHIFT;
@@ -395,8 +417,16 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
   i0 = min(i0, lim); i1 = min(i1, lim); i2 = min(i2, lim); i3 = min(i3, lim);
   const uint32_t idx[4] = {i0, i1, i2, i3};
   float v[4][W];
+  if (T.smem_off >= 0) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) load_slice<W>(base + idx[r], v[r]);
+    for (int r = 0; r < 4; ++r) load_slice<W>(base + idx[r], v[r]);
+  } else if (W == 8 && ld_pol) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ld_na_f256_hint(base + idx[r], v[r], ld_pol);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) load_slice_l2<W>(base + idx[r], v[r]);
+  }
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     float p[4][CT];
@@ -404,7 +434,7 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int t = 0; t < CT; ++t) p[r][t] = v[r][o * CT + t];
-    finish_rows4<CT>(p, bad, false, quad, n_rows, outs.out[o]);
+    finish_rows4<CT>(p, bad, false, quad, n_rows, outs.out[o], st_pol);
   }
 }
 
@@ -420,6 +450,107 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned
   const int64_t nquads = (n_rows + 3) >> 2;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += int64_t(gridDim.x) * blockDim.x)
     gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs);
+}
+
+// ---- tile-staged variant for large batches -------------------------------------------------------------------
+// The evidence columns a plan reads are brought into shared memory by 1-D bulk async copies (TMA engine), one
+// 1024-row tile per stage, GT_STAGES tiles ahead: a thread never waits on DRAM for its codes, so the only exposed
+// latency left is the table gather itself, and the copies keep far more bytes in flight than register loads can.
+constexpr int GT_TILE_ROWS = 4 * GATHER_TPB;    // one quad per thread per tile
+constexpr int GT_MAX_COLS = 16;
+constexpr int GT_MAX_STAGES = 4;
+
+struct TileCols {
+  int n;
+  uint8_t slot[GT_MAX_COLS];     // evidence slot staged as tile column c
+};
+struct TileLoader {
+  const unsigned char* stage;    // [n cols][GT_TILE_ROWS] codes of the current tile; descriptors hold tile columns, not slots
+  int64_t quad0;
+  __device__ __forceinline__ uint32_t load4(int col, int64_t quad) const {
+    return *reinterpret_cast<const uint32_t*>(stage + col * GT_TILE_ROWS + (int(quad - quad0) << 2));
+  }
+};
+
+template <int CT, int NOUT>     // NOUT == 0: generic table list (gather_rows4); NOUT >= 2: one interleaved table
+__global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
+                                                                  int desc_bytes, int n_tables, const __grid_constant__ TileCols cols,
+                                                                  int n_stages, int hints, const uint8_t* __restrict__ ev, int64_t ld,
+                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
+  stage_blob(blob, blob_bytes, smem_raw);
+  GTable* st = reinterpret_cast<GTable*>(smem_raw);
+  // descriptors address evidence slots; inside this kernel they address staged tile columns
+  for (int i = threadIdx.x; i < n_tables * GATHER_MAX_TABLE_EV; i += blockDim.x) {
+    GTable& T = st[i / GATHER_MAX_TABLE_EV];
+    const int j = i % GATHER_MAX_TABLE_EV;
+    if (j < T.n_ev) {
+      int c = 0;
+      while (c < cols.n - 1 && cols.slot[c] != T.slot[j]) ++c;
+      T.slot[j] = (uint8_t)c;
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GATHER_TPB / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float* pool = reinterpret_cast<const float*>(smem_raw + desc_bytes);
+  unsigned char* stages = smem_raw + ((blob_bytes + 127) & ~127);
+  // L2 policy: the streams (codes in, posteriors out) are touched once, the tables are what should stay resident
+  uint64_t pol_first, pol_last;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  const uint64_t st_pol = (hints & 1) ? pol_first : 0, cp_pol = (hints & 2) ? pol_first : 0, ld_pol = (hints & 4) ? pol_last : 0;
+  const uint32_t stage_bytes = uint32_t(cols.n) * GT_TILE_ROWS;
+  const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
+  const int64_t nquads = (n_rows + 3) >> 2;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int lane = threadIdx.x & 31;
+
+  auto issue = [&](int64_t i) {    // warp 0: fill stage i % n_stages with this CTA's i-th tile
+    const int s = int(i % n_stages);
+    const int64_t row0 = (int64_t(blockIdx.x) + i * gridDim.x) * GT_TILE_ROWS;
+    const uint32_t bytes = (uint32_t)min((long long)GT_TILE_ROWS, (long long)(((n_rows - row0) + 15) & ~int64_t(15)));
+    if (lane == 0) mbar_expect_tx(&full[s], bytes * uint32_t(cols.n));
+    __syncwarp();
+    if (lane < cols.n) {
+      if (cp_pol) bulk_g2s_hint(stages + size_t(s) * stage_bytes + size_t(lane) * GT_TILE_ROWS, ev + int64_t(cols.slot[lane]) * ld + row0, bytes, &full[s], cp_pol);
+      else bulk_g2s(stages + size_t(s) * stage_bytes + size_t(lane) * GT_TILE_ROWS, ev + int64_t(cols.slot[lane]) * ld + row0, bytes, &full[s]);
+    }
+  };
+  if (threadIdx.x < 32)
+    for (int64_t i = 0; i < my_tiles && i < n_stages - 1; ++i) issue(i);
+
+  for (int64_t i = 0; i < my_tiles; ++i) {
+    const int s = int(i % n_stages);
+    const uint32_t round = uint32_t(i / n_stages);
+    // refill the stage that tile i-1 used (every warp released it one iteration ago) with tile i-1+n_stages
+    if (threadIdx.x < 32) {
+      const int64_t nxt = i + n_stages - 1;
+      if (nxt < my_tiles) {
+        if (i > 0) mbar_wait(&empty[(i - 1) % n_stages], uint32_t((i - 1) / n_stages) & 1u);
+        issue(nxt);
+      }
+    }
+    mbar_wait(&full[s], round & 1u);
+    const int64_t tile = int64_t(blockIdx.x) + i * gridDim.x;
+    const int64_t q0 = tile * (GT_TILE_ROWS / 4);
+    const int64_t q = q0 + threadIdx.x;
+    TileLoader L{stages + size_t(s) * stage_bytes, q0};
+    if (q < nquads) {
+      if constexpr (NOUT >= 2) {
+        const GTable& T = st[0];
+        const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
+        gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs, st_pol, ld_pol);
+      } else {
+        gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs, st_pol);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
 }
 
 constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 6 : (ct <= 4 ? 5 : 3); }
@@ -721,10 +852,74 @@ int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   return CBN_OK;
 }
 
+// tile-staged launch: persistent CTAs, as many as fit per SM for this plan's shared-memory footprint
+template <int CT, int NOUT>
+int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
+                 cudaStream_t s) {
+  TileCols cols{};
+  for (const GTable& t : p->h_tables)
+    for (int j = 0; j < t.n_ev; ++j) {
+      int c = 0;
+      while (c < cols.n && cols.slot[c] != t.slot[j]) ++c;
+      if (c == cols.n) cols.slot[cols.n++] = t.slot[j];
+    }
+  const size_t blob_pad = (p->blob_bytes + 127) & ~size_t(127);
+  const size_t stage_bytes = size_t(cols.n) * GT_TILE_ROWS;
+  // as many stages as the shared memory of one SM allows at the occupancy the registers were bounded for
+  // three stages: deeper prefetch only takes shared memory away from L1, which tracks the outstanding table gathers
+  // (measured on B200: 4+ stages are slower)
+  int n_stages = 3;
+  while (n_stages > 2 && blob_pad + n_stages * stage_bytes > 56 * 1024) --n_stages;
+  const int hints = 7;     // evict-first for the code and posterior streams, evict-last for the table
+  const size_t smem = blob_pad + n_stages * stage_bytes;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_tiles_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set[ctx->device & 63] = true;
+  }
+  static size_t occ_smem = ~size_t(0);
+  static int occ = 1;
+  if (occ_smem != smem) {
+    CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_tiles_kernel<CT, NOUT>, GATHER_TPB, smem));
+    occ_smem = smem;
+  }
+  const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
+  const int per_sm = std::max(occ, 1);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, int64_t(ctx->sm_count) * per_sm));
+  gather_tiles_kernel<CT, NOUT><<<blocks, GATHER_TPB, smem, s>>>(p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, cols,
+                                                                 n_stages, hints, ev, ld, n_rows, outs);
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+// large batches go through the tile-staged kernel (CBN_GATHER_TILES=0/1 forces the choice; default: >= 2^22 rows)
+bool use_tiles(const cbn_ve_plan* p, int64_t n_rows) {
+  static int mode = -2;
+  if (mode == -2) { const char* e = getenv("CBN_GATHER_TILES"); mode = e ? atoi(e) : -1; }
+  if (mode == 0 || p->card_t > GATHER_MAX_CT || p->n_evidence < 1) return false;
+  std::vector<char> seen(256, 0);
+  int n = 0;
+  for (const GTable& t : p->h_tables)
+    for (int j = 0; j < t.n_ev; ++j)
+      if (!seen[t.slot[j]]) { seen[t.slot[j]] = 1; ++n; }
+  if (n < 1 || n > GT_MAX_COLS) return false;
+  if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS > 150 * 1024) return false;
+  return mode == 1 || n_rows >= (int64_t(1) << 22);
+}
+
 int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
                       const GatherOuts& outs, cudaStream_t s) {
+  const bool tiles = use_tiles(plan, n_rows);
   if (plan->interleaved) {
     const int key = plan->card_t * 10 + plan->interleaved;
+    if (tiles) switch (key) {
+      case 22: return launch_tiles<2, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 23: return launch_tiles<2, 3>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 24: return launch_tiles<2, 4>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 32: return launch_tiles<3, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      case 42: return launch_tiles<4, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+      default: break;
+    }
     switch (key) {
       case 22: return launch_inter<2, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
       case 23: return launch_inter<2, 3>(ctx, plan, ev_codes, ld, n_rows, outs, s);
@@ -733,6 +928,17 @@ int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_c
       case 42: return launch_inter<4, 2>(ctx, plan, ev_codes, ld, n_rows, outs, s);
       default: return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "internal: interleaved plan %d x %d", plan->card_t, plan->interleaved);
     }
+  }
+  if (tiles) switch (plan->card_t) {
+    case 1: return launch_tiles<1, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 2: return launch_tiles<2, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 3: return launch_tiles<3, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 4: return launch_tiles<4, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 5: return launch_tiles<5, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 6: return launch_tiles<6, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 7: return launch_tiles<7, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    case 8: return launch_tiles<8, 0>(ctx, plan, ev_codes, ld, n_rows, outs, s);
+    default: break;
   }
   switch (plan->card_t) {
     case 1: return launch_codes<1>(ctx, plan, ev_codes, ld, n_rows, outs, s);

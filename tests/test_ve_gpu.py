@@ -214,6 +214,43 @@ def test_fused_multi_target_launch_matches_single_plans():
         infer.fused_plan(["HYPOVOLEMIA", "VENTLUNG"], synth.ALARM_EVIDENCE)
 
 
+def test_tile_staged_kernel_matches_direct_kernel_on_large_batches():
+    """Batches of >= 2^22 rows run through the tile-staged kernel (bulk async copies of the evidence tiles); the
+    same rows answered in smaller calls use the direct kernel: the posteriors must be bit-identical, including the
+    ragged last tile, an unseen code and a slice of the batch checked against the oracle."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.alarm()
+    _, infer = install_cpts(spec, DEV)
+    n = (1 << 22) + 1027
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    rng = np.random.default_rng(9)
+    ev = np.stack([rng.integers(0, spec.cards[i], size=n) for i in ids], axis=1).astype(np.uint8)
+    ev[n - 2, 4] = 255
+    ev[12345, 0] = 255
+    m = _codes_matrix(ev)
+    half = 1 << 21
+    for plan in (infer.fused_plan(synth.ALARM_TARGETS, synth.ALARM_EVIDENCE), infer.plan("VENTLUNG", synth.ALARM_EVIDENCE),
+                 infer.plan("LVFAILURE", synth.ALARM_EVIDENCE[:5])):
+        multi = hasattr(plan, "n_out")
+        big = plan.run_codes(m, n)
+        big = big if multi else [big]
+        for o in big:
+            assert bool((o[n - 2] == 0).all()) and bool((o[12345] == 0).all())
+        for s0 in range(0, n, half):
+            cnt = min(half, n - s0)
+            part = plan.run_codes(m[:, s0:], cnt)            # s0 is a multiple of 16: alignment is preserved
+            part = part if multi else [part]
+            for o, q in zip(big, part):
+                assert torch.equal(o[s0:s0 + cnt], q)
+    net = _net(spec)
+    got = infer.plan("VENTLUNG", synth.ALARM_EVIDENCE).run_codes(m, n)[-600:].cpu().numpy()
+    ok = np.ones(600, bool); ok[600 - 2] = False
+    want = O.ve_posterior(net, spec.names.index("VENTLUNG"), ids, ev[-600:][ok])
+    np.testing.assert_allclose(got[ok], want, rtol=RTOL, atol=1e-30)
+
+
 def test_per_row_executor_matches_oracle():
     """A small table budget forces the per-row elimination schedule (linear-rescaled and log-space)."""
     from continuousbayesiannetwork_b200 import synth
