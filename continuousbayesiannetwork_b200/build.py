@@ -44,7 +44,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("CBN_EXTRA_NVCC", "").split() + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]

@@ -26,10 +26,10 @@
 #include "common.cuh"
 
 namespace {
-constexpr int COUNT_TPB = 256;
-constexpr int TILE = 2048;                 // samples per tile (8 per thread: one 64-bit word per column)
-constexpr int TILE_SHIFT = 11;
-constexpr int MAX_GCOLS = 16;              // columns staged per group (2 x 16 x 2 KB of staging)
+constexpr int COUNT_TPB = 256;             // direct kernel; the tile kernel runs 256-thread (2 per SM) or 512-thread (1 per SM) CTAs
+constexpr int TILE = 2048;                 // samples per tile and staged column (8 per thread: one 64-bit word per column)
+constexpr int MAX_STAGES = 6;              // staged tiles per CTA (the plan picks what fits)
+constexpr int MAX_GCOLS = 32;              // columns staged per group (one bulk copy per lane of warp 0)
 constexpr int MAX_GROUP_CELLS = 8192;      // 32 KB of uint32 counters
 constexpr int MAX_GROUP_FAMS = 64;
 constexpr int MAX_GROUP_ENTRIES = MAX_GROUP_FAMS * 4;
@@ -206,15 +206,18 @@ __device__ __forceinline__ void count_family_tile(const uint32_t* __restrict__ e
   }
 }
 
-// shared memory: [counters][family headers][entry stream][stage 0][stage 1]
-__global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
-    const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, const TileGroup* __restrict__ groups,
+// shared memory: [counters][family headers][entry stream][stage 0]..[stage n_stages-1]
+// n_stages-1 tiles of bulk copies are in flight per CTA (full[] barriers): with two CTAs per SM that is what keeps
+// enough bytes outstanding to cover the HBM latency when a group stages only a few columns.
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 512 / TPB) count_tiles_kernel(
+    const uint8_t* __restrict__ codes, int64_t ld, int64_t n_tiles, int n_groups, int n_stages, int tile_samples,
+    const TileGroup* __restrict__ groups,
     const int* __restrict__ gcols, const uint32_t* __restrict__ entries, const uint4* __restrict__ famhdr,
     const SuperInfo* __restrict__ sinfo, const SuperMember* __restrict__ members, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ int s_cols[MAX_GCOLS];
-  __shared__ int s_next[2];
-  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(8) uint64_t full[MAX_STAGES];
   const int g = blockIdx.x % n_groups;       // groups of one tile are neighbours in launch order (L2 reuse)
   const int64_t x = blockIdx.x / n_groups;
   const int64_t xstride = gridDim.x / n_groups;
@@ -224,48 +227,52 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
   uint4* s_hdr = reinterpret_cast<uint4*>(smem + hdr_off);
   uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem + hdr_off + size_t(G.n_fams) * 16);
   unsigned char* stage = smem + ((hdr_off + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127));
-  const uint32_t tile_bytes = (uint32_t)G.n_cols * TILE;
+  const uint32_t tile_bytes = (uint32_t)G.n_cols * tile_samples;
   for (int i = threadIdx.x; i < G.n_entries; i += blockDim.x) s_ent[i] = entries[G.ent_start + i];
   for (int i = threadIdx.x; i < G.n_fams; i += blockDim.x) s_hdr[i] = famhdr[G.fam_start + i];
   for (int i = threadIdx.x; i < G.n_cells; i += blockDim.x) tbl[i] = 0u;
   if (threadIdx.x < G.n_cols) s_cols[threadIdx.x] = gcols[G.col_start + threadIdx.x];
   if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    s_next[0] = s_next[1] = 0;
+    for (int b = 0; b < n_stages; ++b) mbar_init(&full[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  auto issue = [&](int64_t tile, int b) {   // warp 0 only
-    if (threadIdx.x == 0) mbar_expect_tx(&bar[b], tile_bytes);
-    __syncwarp();
-    if (threadIdx.x < G.n_cols)
-      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(threadIdx.x) * TILE, codes + int64_t(s_cols[threadIdx.x]) * ld + tile * TILE,
-               TILE, &bar[b]);
-  };
-
-  int64_t t = x;
-  int buf = 0;
-  uint32_t phase0 = 0, phase1 = 0;
-  if (t < n_tiles && threadIdx.x < 32) issue(t, 0);
   const int lane = threadIdx.x & 31;
+  const int64_t my_tiles = x < n_tiles ? (n_tiles - x + xstride - 1) / xstride : 0;
+
+  auto issue = [&](int i, int b) {   // warp 0: this CTA's i-th tile into stage b (== i % n_stages)
+    const int64_t tile = x + i * xstride;
+    if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
+    __syncwarp();
+    if (lane < G.n_cols)
+      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(lane) * tile_samples, codes + int64_t(s_cols[lane]) * ld + tile * tile_samples,
+               (uint32_t)tile_samples, &full[b]);
+  };
+  if (threadIdx.x < 32)
+    for (int i = 0; i < my_tiles && i < n_stages - 1; ++i) issue(i, i);
+
   const int n_fams = G.n_fams;
-  // few families: split every family's tile into 2 or 4 parts so the 8 warps stay balanced
-  const int split_log2 = n_fams >= 16 ? 0 : (n_fams >= 8 ? 1 : (n_fams >= 4 ? 2 : 3));
-  for (; t < n_tiles; t += xstride) {
-    const int64_t tn = t + xstride;
-    // the other buffer was released by the __syncthreads that closed the previous iteration
-    if (tn < n_tiles && threadIdx.x < 32) issue(tn, buf ^ 1);
-    if (buf == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
-    const unsigned char* tile = stage + size_t(buf) * tile_bytes;
+  // few families: split every family's tile into 2, 4 or 8 parts so the 8 warps stay balanced
+  // one (family, whole tile) unit per warp is the cheapest schedule (the per-unit dispatch is paid once per tile); a
+  // group with fewer families than warps splits every family's tile until at least 3/4 of the warps have a unit
+  constexpr int N_WARPS = TPB / 32;
+  int split_log2 = 0;
+  while (split_log2 < 3 && (n_fams << split_log2) * 4 < N_WARPS * 3) ++split_log2;
+  const int n_units = n_fams << split_log2;
+  int b = 0, b_fill = n_stages - 1;      // stage of tile i / stage the next copy goes to
+  uint32_t phase = 0;
+  const int n_my = (int)my_tiles;
+  for (int i = 0; i < n_my; ++i) {
+    // the stage tile i-1 used was released by the __syncthreads that closed the previous iteration
+    if (threadIdx.x < 32 && i + n_stages - 1 < n_my) issue(i + n_stages - 1, b_fill);
+    mbar_wait(&full[b], phase);
+    const unsigned char* tile = stage + size_t(b) * tile_bytes;
     // family-stationary: a warp takes (family, part of the tile) units, so the per-family metadata is loop invariant;
-    // units go round-robin over the warps (families are sorted by cost, largest first)
-    const int n_units = n_fams << split_log2;
-    for (int unit = threadIdx.x >> 5; unit < n_units; unit += COUNT_TPB / 32) {
+    // units go round-robin over the warps (families are sorted by cost, largest first), rotated from tile to tile
+    for (int unit = ((threadIdx.x >> 5) + i) & (N_WARPS - 1); unit < n_units; unit += N_WARPS) {
       const int f = unit >> split_log2;
       const int part = unit & ((1 << split_log2) - 1);
-      const int w0 = part * (TILE >> split_log2), w1 = w0 + (TILE >> split_log2);
+      const int w0 = part * (tile_samples >> split_log2), w1 = w0 + (tile_samples >> split_log2);
       const uint4 hdr = s_hdr[f];        // x: table offset, y: n_cells, z: n_lo | n_hi << 8, w: first entry
       uint32_t* tb = tbl + hdr.x;
       const uint32_t nc = hdr.y;
@@ -282,14 +289,15 @@ __global__ void __launch_bounds__(COUNT_TPB, 2) count_tiles_kernel(
         default: count_family_tile<-1, -1>(ent, n_lo, n_hi, tile, w0, w1, tb, nc, lane, info, members, counts); break;
       }
     }
-    __syncthreads();   // every read of this buffer is done before it is refilled
-    buf ^= 1;
+    __syncthreads();   // every read of this stage is done before it is refilled
+    b_fill = b;
+    if (++b == n_stages) { b = 0; phase ^= 1u; }
   }
   // flush: every non-zero cell of a (super-)family table is added to each member family's int64 table at the cell's
   // marginal index (a plain family has one member with identical layout).  Merged tables are first marginalised into
   // shared memory (the staging buffers are free now), so the global atomics are one per member cell, not per super cell.
   uint32_t* scratch = reinterpret_cast<uint32_t*>(stage);
-  const int scratch_cap = int(2 * tile_bytes / 4);
+  const int scratch_cap = int(n_stages * tile_bytes / 4);
   for (int f = 0; f < n_fams; ++f) {
     const uint4 hdr = s_hdr[f];
     const int nc = int(hdr.y);
@@ -399,7 +407,10 @@ struct cbn_count_plan {
   // tile kernel
   int n_groups = 0;
   int ctas_per_sm = 2;
-  size_t tile_smem = 0;
+  int n_stages = 2;
+  int tile_samples = TILE;
+  int tpb = 256;
+  size_t tile_smem = 0, max_stage_bytes = 0;
   TileGroup* d_groups = nullptr;
   int* d_gcols = nullptr;
   uint32_t* d_entries = nullptr;
@@ -450,7 +461,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   for (int f = 0; f < n_fams; ++f) {
     int rc = check_family(ctx, &fams[f], n_cols, &cells[f]);
     if (rc) return rc;
-    (cells[f] <= MAX_GROUP_CELLS && fams[f].n_vars <= MAX_GCOLS ? small : large).push_back(f);
+    (cells[f] <= MAX_GROUP_CELLS ? small : large).push_back(f);
   }
   // ---- merge families into super-families: one shared-memory update per sample then serves several families.
   // Greedy: grow a seed by the family that enlarges the union table the least while it stays <= MERGE_CELLS.
@@ -504,6 +515,11 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     }
   }
   const int n_sup = (int)supers.size();
+  // many tables: 512-thread CTAs (one per SM, 16 tables and up to 32 columns per group -> half as many groups re-reading
+  // columns); few tables: 256-thread CTAs, two per SM
+  int tpb = n_sup > 16 ? 512 : 256;
+  if (const char* env = getenv("CBN_COUNT_TPB")) tpb = atoi(env) == 512 ? 512 : 256;
+  const int max_gcols = tpb == 512 ? 32 : 24;
   // ---- cluster the super-families by column overlap (fewer staged columns per group = less L2 traffic)
   std::vector<std::vector<int>> groups;
   std::vector<std::vector<int>> group_cols;
@@ -511,6 +527,12 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     std::vector<char> used(n_sup, 0);
     int left = n_sup;
     int cursor = 0;
+    // one (family, whole tile) unit per warp and tile is the cheapest schedule: aim at groups of COUNT_TPB/32 tables,
+    // spread evenly (13 tables -> 7 + 6, not 8 + 5)
+    int target = tpb / 32;
+    if (const char* env = getenv("CBN_COUNT_GROUP_FAMS")) target = std::max(1, std::min(MAX_GROUP_FAMS, atoi(env)));
+    const int n_target_groups = (n_sup + target - 1) / target;
+    int groups_left = n_target_groups;
     auto alloc_of = [&](int q) { return std::max<int64_t>(supers[q].cells + 1, 256); };   // shared-memory cells a table takes
     while (left > 0) {
       while (used[cursor]) ++cursor;
@@ -520,14 +542,16 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
       int64_t gcells = alloc_of(seed);
       int gentries = (int)supers[seed].vars.size();
       used[seed] = 1; --left;
-      while (left > 0 && (int)members.size() < MAX_GROUP_FAMS) {
+      const int want = groups_left > 0 ? (left + 1 + groups_left - 1) / groups_left : target;   // left + 1 counts the seed
+      if (groups_left > 0) --groups_left;
+      while (left > 0 && (int)members.size() < std::min(MAX_GROUP_FAMS, want)) {
         int best = -1, best_new = 1 << 30, best_shared = -1;
         for (int q = 0; q < n_sup; ++q) {
           if (used[q] || gcells + alloc_of(q) > MAX_GROUP_CELLS + MAX_GROUP_FAMS ||
               gentries + (int)supers[q].vars.size() > MAX_GROUP_ENTRIES) continue;
           int nnew = 0, shared = 0;
           for (int v : supers[q].vars) (cols.count(v) ? shared : nnew)++;
-          if ((int)cols.size() + nnew > MAX_GCOLS) continue;
+          if ((int)cols.size() + nnew > max_gcols) continue;
           if (nnew < best_new || (nnew == best_new && shared > best_shared)) { best = q; best_new = nnew; best_shared = shared; }
         }
         if (best < 0) break;
@@ -548,13 +572,32 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
   p->n_groups = (int)groups.size(); p->n_small = (int)small.size(); p->n_large = (int)large.size();
   p->n_supers = n_sup;
 
+  // tile size: as large as 32 KB of staging per tile allows for the widest group (more work per block barrier)
+  int tile_samples = TILE;
+  {
+    size_t widest = 1;
+    for (auto& gc : group_cols) widest = std::max(widest, gc.size());
+    int max_tile = 8192;
+    if (const char* env = getenv("CBN_COUNT_TILE")) max_tile = std::max(TILE, std::min(16384, atoi(env)));
+    while (tile_samples * 2 <= max_tile && widest * size_t(tile_samples) * 2 <= 32 * 1024) tile_samples *= 2;
+    // two 256-thread CTAs per SM need <= ~110 KB each: large tables + wide groups fall back to 1024-sample tiles
+    size_t table_bytes = 0;
+    for (auto& gm : groups) {
+      size_t b = 0;
+      for (int q : gm) b += size_t(std::max<int64_t>(supers[q].cells + 1, 256)) * 4 + 64;
+      table_bytes = std::max(table_bytes, b);
+    }
+    if (tpb == 256 && table_bytes + 2 * widest * size_t(tile_samples) > 110 * 1024) tile_samples = 1024;
+  }
+  p->tile_samples = tile_samples;
+  p->tpb = tpb;
   std::vector<TileGroup> h_groups;
   std::vector<int> h_gcols;
   std::vector<uint32_t> h_entries;
   std::vector<uint4> h_famhdr;
   std::vector<SuperInfo> h_sinfo;
   std::vector<SuperMember> h_members;
-  size_t tile_smem = 0;
+  size_t tile_smem = 0, max_stage_bytes = 0;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     TileGroup G{};
     G.fam_start = (int)h_famhdr.size(); G.n_fams = (int)groups[gi].size();
@@ -574,7 +617,7 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
         sstride[j] = st;
         reach += int64_t(S.cards[j] - 1) * st;
         if (reach > 255 || n_hi > 0) ++n_hi; else ++n_lo;
-        h_entries.push_back((uint32_t(st) << 16) | uint32_t(local * TILE));
+        h_entries.push_back((uint32_t(st) << 16) | uint32_t(local * tile_samples));
         st *= S.cards[j];
       }
       h_famhdr.push_back(make_uint4(uint32_t(off), uint32_t(S.cells), uint32_t(n_lo) | (uint32_t(n_hi) << 8), uint32_t(ent_first)));
@@ -606,8 +649,9 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     G.n_cells = off;
     for (int c : group_cols[gi]) h_gcols.push_back(c);
     h_groups.push_back(G);
-    size_t sm = ((((size_t(off) * 4 + 15) & ~size_t(15)) + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127)) + 2 * size_t(G.n_cols) * TILE;
-    tile_smem = std::max(tile_smem, sm);
+    size_t sm = ((((size_t(off) * 4 + 15) & ~size_t(15)) + size_t(G.n_fams) * 16 + size_t(G.n_entries) * 4 + 127) & ~size_t(127));
+    tile_smem = std::max(tile_smem, sm);                 // tables + metadata; the stages are added below
+    max_stage_bytes = std::max(max_stage_bytes, size_t(G.n_cols) * tile_samples);
   }
   // ---- direct kernel (tail samples): the original small families, packed into shared-memory sized groups
   std::vector<long long> h_goff;       // record order = direct groups, then large families
@@ -646,6 +690,20 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     h_goff.push_back(F.table_offset);
   }
   p->group_start = h_group_start;
+  // as many stages as two CTAs per SM leave room for (at least double buffering)
+  {
+    int stages = 2;
+    if (const char* env = getenv("CBN_COUNT_STAGES")) stages = std::max(2, std::min(MAX_STAGES, atoi(env)));
+    else while (stages < 4 && tile_smem + size_t(stages + 1) * max_stage_bytes <= size_t(200 * 1024) / (512 / tpb)) ++stages;
+    p->n_stages = stages;
+    tile_smem += size_t(stages) * max_stage_bytes;
+  }
+  if (getenv("CBN_COUNT_DEBUG")) {
+    fprintf(stderr, "count plan: %d families -> %d tables -> %d groups, tile %d samples, %d stages, %zu B shared memory\n", n_fams, n_sup,
+            (int)groups.size(), tile_samples, p->n_stages, tile_smem);
+    for (size_t gi = 0; gi < h_groups.size(); ++gi)
+      fprintf(stderr, "  group %2zu: %2d tables %2d cols %5d cells %3d entries\n", gi, h_groups[gi].n_fams, h_groups[gi].n_cols, h_groups[gi].n_cells, h_groups[gi].n_entries);
+  }
   p->tile_smem = tile_smem; p->direct_smem = direct_smem;
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(&p->d_groups, h_groups);
@@ -668,9 +726,14 @@ extern "C" int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32
     if (e == cudaSuccess) e = upload(&p->d_cpt, h_cpt);
   }
   if (e == cudaSuccess && p->n_groups > 0) {
-    e = cudaFuncSetAttribute(count_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
     int occ = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_tiles_kernel, COUNT_TPB, tile_smem);
+    if (tpb == 512) {
+      e = cudaFuncSetAttribute(count_tiles_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_tiles_kernel<512>, 512, tile_smem);
+    } else {
+      e = cudaFuncSetAttribute(count_tiles_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_tiles_kernel<256>, 256, tile_smem);
+    }
     p->ctas_per_sm = std::max(1, occ);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(count_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)direct_smem);
@@ -700,18 +763,22 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
   for (int64_t start = 0; start < n; start += chunk) {
     const int64_t m = std::min(chunk, n - start);  // start is a multiple of 2^33: alignment is preserved
     const uint8_t* base = codes + start;
-    const int64_t n_tiles = m / TILE;
-    const int64_t tail = m - n_tiles * TILE;
+    const int64_t n_tiles = m / plan->tile_samples;
+    const int64_t tail = m - n_tiles * plan->tile_samples;
     if (plan->n_groups > 0) {
       if (n_tiles > 0) {
         int per_group = (int)std::min<int64_t>(n_tiles, std::max(1, (plan->ctas_per_sm * plan->sm_count) / plan->n_groups));
-        count_tiles_kernel<<<per_group * plan->n_groups, COUNT_TPB, plan->tile_smem, s>>>(
-            base, ld, n_tiles, plan->n_groups, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_sinfo, plan->d_members, counts);
+        if (plan->tpb == 512)
+          count_tiles_kernel<512><<<per_group * plan->n_groups, 512, plan->tile_smem, s>>>(
+              base, ld, n_tiles, plan->n_groups, plan->n_stages, plan->tile_samples, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_sinfo, plan->d_members, counts);
+        else
+          count_tiles_kernel<256><<<per_group * plan->n_groups, 256, plan->tile_smem, s>>>(
+              base, ld, n_tiles, plan->n_groups, plan->n_stages, plan->tile_samples, plan->d_groups, plan->d_gcols, plan->d_entries, plan->d_famhdr, plan->d_sinfo, plan->d_members, counts);
         CBN_CHECK_LAUNCH(ctx);
       }
       if (tail > 0) {
         dim3 grid((unsigned)((tail + COUNT_TPB - 1) / COUNT_TPB), plan->n_direct_groups);
-        count_direct_kernel<false><<<grid, COUNT_TPB, plan->direct_smem, s>>>(base + n_tiles * TILE, ld, tail, plan->d_recs,
+        count_direct_kernel<false><<<grid, COUNT_TPB, plan->direct_smem, s>>>(base + n_tiles * plan->tile_samples, ld, tail, plan->d_recs,
                                                                                plan->d_group_start, 0, plan->d_goff, counts);
         CBN_CHECK_LAUNCH(ctx);
       }
