@@ -227,7 +227,7 @@ def run_ours(args):
     fit_codes = sample_network(spec, seed=1235, first=s, n=e - s, device=dev, tables=tables)
     torch.cuda.synchronize()
 
-    # throughput is measured on a larger resident block (2^26 samples per GPU, 512 MB of codes > L2) ...
+    # throughput is measured on a larger resident block (2^28 samples per GPU, 2 GB of codes >> L2) ...
     n_big = args.fit_samples
     big_tables = tables_from_spec(spec, dev)
     big_codes = sample_network(spec, seed=1235, first=n_fit + rank * n_big, n=n_big, device=dev, tables=big_tables)
@@ -417,7 +417,7 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
     import torch
 
     from continuousbayesiannetwork_b200 import sharding, synth
-    from continuousbayesiannetwork_b200.engine import install_cpts, sample_network, tables_from_spec
+    from continuousbayesiannetwork_b200.engine import bind_inference, install_cpts, sample_network, tables_from_spec
 
     out = {}
     # config 3: Alarm-shaped, 16M evidence rows sharded over the ranks (strong scaling inside this extra)
@@ -448,7 +448,7 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
                     "frac_of_hbm_peak": alg * k / sec / 1e9 / (peak_gbs * world), "plan_compile_ms": compile_ms,
                     "table_cells": [p.stats.final_tables[0][1] for p in plans]}
     # config 3, fit half: counting on the Alarm structure
-    n_chunk = args.fit_chunk
+    n_chunk = 2 * args.fit_chunk
     codes = sample_network(spec, seed=1236, first=rank * n_chunk, n=n_chunk, device=dev, tables=tables)
     ftab = tables_from_spec(spec, dev)
     torch.cuda.synchronize()
@@ -485,6 +485,35 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
                            "samples_per_gpu_per_step": n_chunk, "family_groups": tables.count_groups(),
                            "table_updates_per_sample": tables.count_updates_per_sample(),
                            "achieved_GBs": rate * spec.n / 1e9, "frac_of_hbm_peak": rate * spec.n / 1e9 / (peak_gbs * world)}
+    # config 4 (query half): 8 patterns = random target + 10 random evidence variables, 1,048,576 rows each
+    import numpy as np
+
+    infer = bind_inference(tables)
+    rng = np.random.default_rng(1240)
+    rows = 1 << 20
+    full = sample_network(spec, seed=1241, first=rank * rows, n=rows, device=dev, tables=tables)
+    t0 = time.perf_counter()
+    pats = []
+    for _ in range(8):
+        vs = [int(v) for v in rng.choice(spec.n, size=11, replace=False)]
+        plan = infer.plan(spec.names[vs[0]], [spec.names[v] for v in vs[1:]])
+        pats.append((plan, full[vs[1:]].contiguous(), torch.empty((rows, plan.card_t), dtype=torch.float32, device=dev)))
+    torch.cuda.synchronize()
+    compile_ms = (time.perf_counter() - t0) * 1e3
+    del full
+
+    def qstep(_i):
+        for plan, ev, o in pats:
+            plan.run_codes(ev, rows, out=o)
+
+    k = max(3, min(args.steps, 10))
+    sec = timed(qstep, k, 3)
+    alg = sum(rows * p.algorithmic_bytes_per_row() for p, _, _ in pats) * world
+    out["ktree200_ve"] = {"metric": METRIC, "value": rows * len(pats) * world * k / sec, "unit": "queries/s",
+                          "rows_per_gpu_per_pattern": rows, "patterns": len(pats), "achieved_GBs": alg * k / sec / 1e9,
+                          "frac_of_hbm_peak": alg * k / sec / 1e9 / (peak_gbs * world), "plan_compile_ms_total": compile_ms,
+                          "table_cells": [p.stats.final_tables[0][1] for p, _, _ in pats],
+                          "per_row_hidden": [p.stats.per_row_hidden for p, _, _ in pats]}
     return out
 
 
@@ -495,8 +524,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
-    ap.add_argument("--fit-chunk", type=int, default=1 << 24)
-    ap.add_argument("--fit-samples", type=int, default=1 << 26)
+    ap.add_argument("--fit-chunk", type=int, default=1 << 25)
+    ap.add_argument("--fit-samples", type=int, default=1 << 28)
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--graph-streams", type=int, default=3)
     ap.add_argument("--no-extras", action="store_true")

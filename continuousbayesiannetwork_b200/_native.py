@@ -103,6 +103,7 @@ SIGNATURES = {
     "cbn_count_plan_updates_per_sample": (C.c_int, [_P]),
     "cbn_cpt_from_counts": (C.c_int, [_P, _P, C.POINTER(Family), C.c_int32, C.c_longlong, _P, _P, _P]),
     "cbn_cpt_from_plan": (C.c_int, [_P, _P, _P, C.c_longlong, _P, _P, _P]),
+    "cbn_cpt_from_plan_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "cbn_mle_from_counts": (C.c_int, [_P, _P, C.POINTER(Family), C.POINTER(_P), C.c_longlong, _P, _P, _P]),
     "cbn_get_prob_f32": (C.c_int, [_P, _P, C.POINTER(Family), C.POINTER(_P), _P, C.c_int64, C.c_int32, _P,
                                    C.c_int64, _P, _P]),

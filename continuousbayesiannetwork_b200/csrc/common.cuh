@@ -71,7 +71,7 @@ struct CptFam {
   int card;     // node cardinality
 };
 int cbn_launch_cpt_kernel(cbn_ctx* ctx, const long long* counts, const CptFam* d_fams, int n_fams, int max_rows,
-                          long long n_total, float* joint, float* cond, cudaStream_t s);
+                          long long n_total, const long long* n_total_dev, float* joint, float* cond, cudaStream_t s);
 
 // validates one family descriptor; returns its table size
 static inline int check_family(cbn_ctx* ctx, const cbn_family* f, int n_cols, int64_t* n_cells_out) {

@@ -798,5 +798,13 @@ extern "C" int cbn_cpt_from_plan(cbn_ctx* ctx, const cbn_count_plan* plan, const
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_cpt_from_plan: ctx is NULL");
   if (!plan || !counts || n_total < 1 || (!joint && !cond)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_cpt_from_plan: bad argument");
   DeviceGuard g(ctx->device);
-  return cbn_launch_cpt_kernel(ctx, counts, plan->d_cpt, plan->n_fams, plan->cpt_max_rows, n_total, joint, cond, (cudaStream_t)stream);
+  return cbn_launch_cpt_kernel(ctx, counts, plan->d_cpt, plan->n_fams, plan->cpt_max_rows, n_total, nullptr, joint, cond, (cudaStream_t)stream);
+}
+
+extern "C" int cbn_cpt_from_plan_dev(cbn_ctx* ctx, const cbn_count_plan* plan, const long long* counts, const long long* n_total_dev,
+                                     float* joint, float* cond, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_cpt_from_plan_dev: ctx is NULL");
+  if (!plan || !counts || !n_total_dev || (!joint && !cond)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_cpt_from_plan_dev: bad argument");
+  DeviceGuard g(ctx->device);
+  return cbn_launch_cpt_kernel(ctx, counts, plan->d_cpt, plan->n_fams, plan->cpt_max_rows, 1, n_total_dev, joint, cond, (cudaStream_t)stream);
 }

@@ -244,8 +244,10 @@ extern "C" int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const f
 namespace {
 __global__ void __launch_bounds__(256) cpt_from_counts_kernel(const long long* __restrict__ counts,
                                                               const CptFam* __restrict__ fams, float n_total,
+                                                              const long long* __restrict__ n_total_dev,
                                                               float* __restrict__ joint, float* __restrict__ cond) {
   const CptFam f = fams[blockIdx.y];
+  if (n_total_dev) n_total = __ll2float_rn(*n_total_dev);   // the sample count sits on the device (after an all-reduce)
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < f.n_rows; r += gridDim.x * blockDim.x) {
     const long long base = f.off + (long long)r * f.card;
     float parent = 0.0f;
@@ -290,7 +292,7 @@ extern "C" int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const 
   for (int f0 = 0; f0 < n_fams; f0 += 65535) {
     int nf = std::min(65535, n_fams - f0);
     dim3 grid(std::min((max_rows + 255) / 256, 1024), nf);
-    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d + f0, (float)n_total, joint, cond);
+    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d + f0, (float)n_total, nullptr, joint, cond);
   }
   CBN_CHECK_LAUNCH(ctx);
   CBN_CUDA(ctx, cudaFreeAsync(d, s));
@@ -298,11 +300,11 @@ extern "C" int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const 
 }
 
 int cbn_launch_cpt_kernel(cbn_ctx* ctx, const long long* counts, const CptFam* d_fams, int n_fams, int max_rows,
-                          long long n_total, float* joint, float* cond, cudaStream_t s) {
+                          long long n_total, const long long* n_total_dev, float* joint, float* cond, cudaStream_t s) {
   for (int f0 = 0; f0 < n_fams; f0 += 65535) {
     int nf = std::min(65535, n_fams - f0);
     dim3 grid(std::min((max_rows + 255) / 256, 1024), nf);
-    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d_fams + f0, (float)n_total, joint, cond);
+    cpt_from_counts_kernel<<<grid, 256, 0, s>>>(counts, d_fams + f0, (float)n_total, n_total_dev, joint, cond);
   }
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;

@@ -52,7 +52,9 @@ def global_rows(local_rows: int, device=None) -> int:
 def fit_sharded(tables, codes: torch.Tensor, n_local: int):
     """Count the local shard, all-reduce the tables, normalise with the GLOBAL sample count."""
     tables.count(codes, n_local)
-    allreduce_counts(tables.counts)
-    tables.n_total = global_rows(tables.n_total, device=tables.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # tables and sample count travel together: one collective, no host synchronisation
+        allreduce_counts(tables.allreduce_buffer())
+        tables.mark_reduced()
     tables.finalize()
     return tables

@@ -36,7 +36,9 @@ class DiscreteTables:
                 raise ValueError(f"node {n} has {len(ps)} parents; at most {N.MAX_FAMILY_VARS - 1} are supported")
         self.domains: List[Optional[torch.Tensor]] = [None] * len(self.names)   # float32 [card], sorted
         self.cards: List[int] = [0] * len(self.names)
-        self.n_total = 0
+        self._n_host = 0                 # samples counted so far; mirrored on the device next to the tables
+        self._n_host_valid = True
+        self._n_dev: Optional[torch.Tensor] = None
         self.fams = None
         self.offsets: List[int] = []
         self.n_cells: List[int] = []
@@ -80,10 +82,34 @@ class DiscreteTables:
             off += _round_up(cells, 4)      # keep every table 16-byte aligned as float32
         self.fams = fams
         self.total_cells = off
-        self.counts = torch.zeros(off, dtype=torch.int64, device=self.device)
+        # the sample count lives right behind the tables, so a sharded fit moves both with ONE all-reduce and the
+        # normalisation kernel reads it on the device (no host round trip)
+        self._counts_buf = torch.zeros(off + 2, dtype=torch.int64, device=self.device)
+        self.counts = self._counts_buf[:off]
+        self._n_dev = self._counts_buf[off:off + 1]
         self.joint = None
         self.cond = None
-        self.n_total = 0
+        self._n_host, self._n_host_valid = 0, True
+
+    @property
+    def n_total(self) -> int:
+        """Samples behind the current tables (global after a sharded fit)."""
+        if not self._n_host_valid:
+            self._n_host, self._n_host_valid = int(self._n_dev.item()), True
+        return self._n_host
+
+    @n_total.setter
+    def n_total(self, v: int):
+        self._n_host, self._n_host_valid = int(v), True
+        if self._n_dev is not None:
+            self._n_dev.fill_(int(v))
+
+    def allreduce_buffer(self) -> torch.Tensor:
+        """Tables + sample count as one int64 tensor; after summing it over the ranks call ``mark_reduced``."""
+        return self._counts_buf
+
+    def mark_reduced(self):
+        self._n_host_valid = False
 
     def _destroy_plan(self):
         if self._count_plan is not None:
@@ -148,7 +174,9 @@ class DiscreteTables:
         self._ensure_plan()
         N.check(lib.cbn_count_run(self.ctx.handle, self._count_plan, codes.data_ptr(), codes.stride(0), int(n),
                                   self.counts.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
-        self.n_total += int(n)
+        self._n_dev.add_(int(n))
+        if self._n_host_valid:
+            self._n_host += int(n)
 
     def _ensure_plan(self):
         if self._count_plan is None:
@@ -166,14 +194,14 @@ class DiscreteTables:
 
     def finalize(self):
         """counts -> joint (fp32(c)/fp32(n)) and cond (joint / (parent + 1e-10))."""
-        if self.n_total < 1:
+        if self._n_host_valid and self._n_host < 1:
             raise ValueError("no samples counted")
         if self.joint is None or self.cond is None:
             self.joint = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
             self.cond = torch.zeros(self.total_cells, dtype=torch.float32, device=self.device)
         self._ensure_plan()
-        N.check(N.lib().cbn_cpt_from_plan(self.ctx.handle, self._count_plan, self.counts.data_ptr(), self.n_total,
-                                          self.joint.data_ptr(), self.cond.data_ptr(), N.stream_ptr(self.device)),
+        N.check(N.lib().cbn_cpt_from_plan_dev(self.ctx.handle, self._count_plan, self.counts.data_ptr(), self._n_dev.data_ptr(),
+                                              self.joint.data_ptr(), self.cond.data_ptr(), N.stream_ptr(self.device)),
                 self.ctx.handle)
 
     def set_cond_tables(self, cpts: Sequence):

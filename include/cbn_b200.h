@@ -125,6 +125,11 @@ CBN_API int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const cbn
 CBN_API int cbn_cpt_from_plan(cbn_ctx* ctx, const cbn_count_plan* plan, const long long* counts, long long n_total,
                       float* joint, float* cond, cbn_stream stream);
 
+/* same, with the global sample count read from device memory: after the int64 all-reduce of a sharded fit
+ * (counts and the sample count travel in one buffer) no host synchronisation is needed before normalising */
+CBN_API int cbn_cpt_from_plan_dev(cbn_ctx* ctx, const cbn_count_plan* plan, const long long* counts,
+                          const long long* n_total_dev, float* joint, float* cond, cbn_stream stream);
+
 /* The reference's sparse `mle_tensor` (brute_force.py:45-53) of ONE family: rows
  * [pa_1..pa_P, x, prob] for the non-zero cells, in lexicographic order.
  * counts: that family's table (already offset).  domains: host array of n_vars device

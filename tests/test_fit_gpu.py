@@ -202,3 +202,29 @@ def test_unseen_codes_are_skipped_not_corrupting():
     t.count(cm, 7)
     assert t.table_view(t.counts, "a").cpu().tolist() == [2, 2, 2]
     assert t.table_view(t.counts, "b").cpu().tolist() == [[1, 1], [1, 1], [0, 1]]
+
+
+def test_sample_count_lives_on_the_device_next_to_the_tables():
+    """Sharded fits all-reduce tables and sample count in one buffer; the normalisation reads the count on the device.
+    Single process here: the buffer layout, the lazy host view and accumulation over calls."""
+    from continuousbayesiannetwork_b200 import sharding, synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+
+    spec = synth.asia()
+    t = tables_from_spec(spec, DEV)
+    codes = sample_network(spec, seed=11, first=0, n=5000, device=DEV, tables=t)
+    sharding.fit_sharded(t, codes, 3000)
+    assert t.n_total == 3000 and int(t.allreduce_buffer()[t.total_cells].item()) == 3000
+    sharding.fit_sharded(t, codes[:, 3008:], 1992)        # accumulates (update_knowledge path)
+    t.mark_reduced()                                      # as after an all-reduce: the host copy is stale
+    assert t.n_total == 4992
+    ref = np.concatenate([synth.sample_forward_numpy(spec, 11, 0, 3000), synth.sample_forward_numpy(spec, 11, 3008, 1992)], axis=1)
+    for i, name in enumerate(spec.names):
+        want = O.dense_counts(ref, spec.parents[i] + [i], spec.cards)
+        assert np.array_equal(t.table_view(t.counts, name).cpu().numpy(), want)
+        j, c = O.cpt_from_counts(want, 4992)
+        assert np.array_equal(t.table_view(t.cond, name).cpu().numpy(), c)
+    t.counts.zero_()
+    t.n_total = 0
+    with pytest.raises(ValueError):
+        t.finalize()

@@ -89,6 +89,22 @@ def test_alarm_and_random_dags():
         _check(spec, infer, spec.names[vs[0]], [spec.names[v] for v in vs[1:]], codes[vs[1:]].T)
 
 
+def test_config4_ktree200_patterns():
+    """BASELINE.json configs[3], query half: 200-node card-4 partial 8-tree, random target + 10 random evidence
+    variables (the 8 patterns bench.py times), against the fp32 and fp64 oracle."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.random_ktree_dag()
+    _, infer = install_cpts(spec, DEV)
+    codes = synth.sample_forward_numpy(spec, 1241, 0, 130)
+    rng = np.random.default_rng(1240)
+    for _ in range(8):
+        vs = [int(v) for v in rng.choice(spec.n, size=11, replace=False)]
+        plan, _ = _check(spec, infer, spec.names[vs[0]], [spec.names[v] for v in vs[1:]], codes[vs[1:]].T)
+        assert plan.stats.per_row_hidden == 0 and plan.stats.max_table_cells <= 1 << 28
+
+
 def test_wide_target_and_mixed_cards():
     from continuousbayesiannetwork_b200 import synth
     from continuousbayesiannetwork_b200.engine import install_cpts
