@@ -262,6 +262,70 @@ class RowPlan:
         return self.run_codes(codes, n_rows, out)
 
 
+class _Greedy:
+    """Greedy min-size elimination with incremental bookkeeping: the scope a variable's elimination would create is
+    cached and only recomputed for the variables that share a factor with the one just eliminated (the full rescan is
+    quadratic in the number of hidden variables: minutes on the 1000-node configuration)."""
+
+    def __init__(self, cards, scopes: Dict[int, List[int]], hidden: Sequence[int], count=None):
+        self.cards = cards
+        self.scopes = {k: list(v) for k, v in scopes.items()}          # factor key -> scope
+        self.count = count if count is not None else (lambda v: True)   # which axes count towards the size
+        self.by_var: Dict[int, set] = {}
+        for k, sc in self.scopes.items():
+            for v in sc:
+                self.by_var.setdefault(v, set()).add(k)
+        self.hidden = set(hidden)
+        self.cost: Dict[int, tuple] = {v: self._cost(v) for v in self.hidden}
+
+    def _cost(self, v):
+        sc = set()
+        for k in self.by_var.get(v, ()):
+            sc.update(self.scopes[k])
+        sc.discard(v)
+        c = 1
+        for u in sc:
+            if self.count(u):
+                c *= self.cards[u]
+        return c, sc
+
+    def best(self):
+        """(variable, size of the table its elimination creates, scope of that table) with the smallest size."""
+        v = min(self.hidden, key=lambda x: (self.cost[x][0], x))
+        c, sc = self.cost[v]
+        return v, c, sc
+
+    def touching(self, v) -> List:
+        return sorted(self.by_var.get(v, ()), key=lambda k: (str(type(k)), k))
+
+    def eliminate(self, v, new_key, new_scope: Sequence[int]):
+        """Remove ``v`` and the factors that mention it; add the factor ``new_key`` over ``new_scope``."""
+        for k in list(self.by_var.get(v, ())):
+            for u in self.scopes[k]:
+                self.by_var[u].discard(k)
+            del self.scopes[k]
+        self.by_var.pop(v, None)
+        self.hidden.discard(v)
+        self.cost.pop(v, None)
+        self.add(new_key, new_scope)
+
+    def add(self, key, scope: Sequence[int]):
+        self.scopes[key] = list(scope)
+        for u in scope:
+            self.by_var.setdefault(u, set()).add(key)
+        for u in scope:
+            if u in self.hidden:
+                self.cost[u] = self._cost(u)
+
+    def replace(self, old_keys, new_key, new_scope):
+        """Pre-multiplication: several factors become one over the union scope (no variable disappears)."""
+        for k in old_keys:
+            for u in self.scopes[k]:
+                self.by_var[u].discard(k)
+            del self.scopes[k]
+        self.add(new_key, new_scope)
+
+
 class VECompiler:
     """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
 
@@ -349,6 +413,9 @@ class VECompiler:
         key = (T, tuple(E), tuple(sorted(D)))
         if not dry and key in self._cache:
             return self._cache[key]
+        if not dry:
+            # structure-only pass first: a query that does not fit fails here, before any table is contracted
+            self.compile(target, evidence, do=do, dry=True)
         Eset = set(E)
         order_key = {v: i for i, v in enumerate(E)}
         stats = PlanStats()
@@ -456,8 +523,9 @@ class VECompiler:
         """Evidence-symbolic elimination.  With ``partial`` the loop stops when the cheapest step exceeds the table
         budget and returns ``(factors, remaining_hidden)`` for the per-row executor instead of raising."""
         cards = self.t.cards
-        factors = list(factors)
-        hidden = list(hidden)
+        live: Dict[int, Factor] = dict(enumerate(factors))
+        next_key = len(factors)
+        g = _Greedy(cards, {k: f.scope for k, f in live.items()}, hidden)
 
         def cells(scope):
             s = 1
@@ -465,42 +533,45 @@ class VECompiler:
                 s *= cards[v]
             return s
 
-        while hidden:
-            best, best_cost, best_scope = None, None, None
-            for v in hidden:
-                scope = set()
-                for f in factors:
-                    if v in f.scope:
-                        scope |= set(f.scope)
-                scope.discard(v)
-                c = cells(scope)
-                if best_cost is None or c < best_cost:
-                    best, best_cost, best_scope = v, c, scope
+        while g.hidden:
+            v, best_cost, best_scope = g.best()
             if best_cost > self.table_budget and partial:
-                return factors, hidden
+                return list(live.values()), sorted(g.hidden)
             if best_cost > self.table_budget:
                 raise PlanTooLarge(
                     f"eliminating the cheapest hidden variable needs a table of {best_cost} cells "
                     f"(budget {self.table_budget}); this query needs the per-row executor")
-            v = best
-            hidden.remove(v)
-            touching = [f for f in factors if v in f.scope]
-            factors = [f for f in factors if v not in f.scope]
+            keys = g.touching(v)
+            touching = [live[k] for k in keys]
             # the kernel multiplies at most MAX_CONTRACT_INPUTS factors at once: pre-multiply the smallest ones
             while len(touching) > N.MAX_CONTRACT_INPUTS:
-                touching.sort(key=lambda f: f.size(cards))
-                a, b = touching[0], touching[1]
+                order = sorted(range(len(touching)), key=lambda i: touching[i].size(cards))
+                ia, ib = order[0], order[1]
+                a, b = touching[ia], touching[ib]
                 sc = sort_scope(a.scope + b.scope)
                 if cells(sc) > self.table_budget:
                     raise PlanTooLarge("pre-multiplication exceeds the table budget")
                 stats.contraction_madds += 2 * cells(sc)
-                touching = touching[2:] + [self._contract([a, b], sc, None, dry)]
+                prod = self._contract([a, b], sc, None, dry)
+                g.replace([keys[ia], keys[ib]], next_key, sc)
+                for k in (keys[ia], keys[ib]):
+                    del live[k]
+                live[next_key] = prod
+                keys = [k for i, k in enumerate(keys) if i not in (ia, ib)] + [next_key]
+                touching = [f for i, f in enumerate(touching) if i not in (ia, ib)] + [prod]
+                next_key += 1
             out_scope = sort_scope(best_scope)
             stats.n_steps += 1
             stats.max_table_cells = max(stats.max_table_cells, best_cost)
             stats.contraction_madds += best_cost * cards[v] * len(touching)
-            factors.append(self._contract(touching, out_scope, v, dry))
-        return (factors, []) if partial else factors
+            res = self._contract(touching, out_scope, v, dry)
+            for k in keys:
+                del live[k]
+            live[next_key] = res
+            g.eliminate(v, next_key, out_scope)
+            next_key += 1
+        out = list(live.values())
+        return (out, []) if partial else out
 
     # ---------------------------------------------------------------- per-row schedule
     def _row_plan(self, T: int, E: List[int], statics: List[Factor], hidden: List[int], stats: PlanStats, dry: bool):
@@ -530,7 +601,14 @@ class VECompiler:
         def emit(inputs, out_scope, sum_var):
             nonlocal off_at, temp_total
             out_shape = [cards[v] for v in out_scope]
-            out_size = int(np.prod(out_shape)) if out_shape else 1
+            out_size = 1
+            for c in out_shape:
+                out_size *= c
+            if temp_total + (out_size + 3) // 4 * 4 > self.row_temp_floats:
+                raise PlanTooLarge(
+                    f"per-row elimination needs more than {temp_total + out_size} floats of temporaries per row "
+                    f"(budget {self.row_temp_floats}): the hidden part of this query has too large an induced width "
+                    "for exact inference")
             offs = np.zeros((len(inputs), out_size), dtype=np.int64)
             grids = np.indices(out_shape).reshape(len(out_scope), -1) if out_scope else np.zeros((0, 1), dtype=np.int64)
             for k, (_, _, st) in enumerate(inputs):
@@ -545,10 +623,6 @@ class VECompiler:
             off_at += offs.size
             temp_total += (out_size + 3) // 4 * 4
             stats.contraction_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
-            if temp_total > self.row_temp_floats:
-                raise PlanTooLarge(
-                    f"per-row elimination needs {temp_total} floats of temporaries per row (budget {self.row_temp_floats}): "
-                    "the hidden part of this query has too large an induced width for exact inference")
             return (n_in + len(steps) - 1, list(out_scope), strides_of(out_scope))
 
         def size_of(scope):
@@ -557,30 +631,35 @@ class VECompiler:
                 s *= cards[v]
             return s
 
-        hidden = list(hidden)
-        while hidden:
-            best = None
-            for v in hidden:
-                sc = set()
-                for _, free, _ in rf:
-                    if v in free:
-                        sc |= set(free)
-                sc.discard(v)
-                c = size_of(sc)
-                if best is None or c < best[0]:
-                    best = (c, v, sc)
-            _, v, sc = best
-            hidden.remove(v)
-            touching = [f for f in rf if v in f[1]]
-            rf = [f for f in rf if v not in f[1]]
+        live = dict(enumerate(rf))                      # key -> (input id, free scope, strides)
+        next_key = len(rf)
+        g = _Greedy(cards, {k: f[1] for k, f in live.items()}, hidden)
+        while g.hidden:
+            v, _, sc = g.best()
+            keys = g.touching(v)
+            touching = [live[k] for k in keys]
             out_scope = sorted(sc, key=lambda a: (a == T, a))
             while len(touching) > N.MAX_CONTRACT_INPUTS:       # pre-multiply the two smallest
-                touching.sort(key=lambda f: size_of(f[1]))
-                a, b = touching[0], touching[1]
+                order = sorted(range(len(touching)), key=lambda i: size_of(touching[i][1]))
+                ia, ib = order[0], order[1]
+                a, b = touching[ia], touching[ib]
                 psc = sorted(set(a[1]) | set(b[1]), key=lambda x: (x == T, x))
-                touching = touching[2:] + [emit([a, b], psc, None)]
-            rf.append(emit(touching, out_scope, v))
+                prod = emit([a, b], psc, None)
+                g.replace([keys[ia], keys[ib]], next_key, psc)
+                for k in (keys[ia], keys[ib]):
+                    del live[k]
+                live[next_key] = prod
+                keys = [k for i, k in enumerate(keys) if i not in (ia, ib)] + [next_key]
+                touching = [f for i, f in enumerate(touching) if i not in (ia, ib)] + [prod]
+                next_key += 1
+            res = emit(touching, out_scope, v)
+            for k in keys:
+                del live[k]
+            live[next_key] = res
+            g.eliminate(v, next_key, out_scope)
+            next_key += 1
             stats.n_steps += 1
+        rf = list(live.values())
         # final product over what is left (free scope is empty or [T])
         while len(rf) > N.MAX_CONTRACT_INPUTS:
             rf = rf[N.MAX_CONTRACT_INPUTS:] + [emit(rf[:N.MAX_CONTRACT_INPUTS], [T], None)]

@@ -105,6 +105,34 @@ def test_config4_ktree200_patterns():
         assert plan.stats.per_row_hidden == 0 and plan.stats.max_table_cells <= 1 << 28
 
 
+def test_config5_layered_dag_shallow_patterns():
+    """BASELINE.json configs[4]: the 1000-node layered DAG.  Uniformly random patterns have an induced width far beyond
+    exact inference (test_host_logic.py::test_planner_budget_and_layered_stress); patterns whose target and evidence
+    lie in the first five layers are tractable and exercise both executors (gather plans and per-row elimination)."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+    from continuousbayesiannetwork_b200.ve import PlanTooLarge, RowPlan
+
+    spec = synth.layered_dag()
+    _, infer = install_cpts(spec, DEV)
+    codes = synth.sample_forward_numpy(spec, 1243, 0, 48)
+    rng = np.random.default_rng(1242)
+    kinds = set()
+    done = 0
+    for p in range(64):
+        k = int(rng.integers(5, 51))
+        vs = [int(v) for v in rng.choice(5 * 50, size=k + 1, replace=False)]
+        if p % 8 not in (0, 5):           # a sample of the 64 patterns (the oracle takes seconds per pattern)
+            continue
+        try:
+            plan, _ = _check(spec, infer, spec.names[vs[0]], [spec.names[v] for v in vs[1:]], codes[vs[1:]].T, truth64=False)
+        except PlanTooLarge:
+            continue
+        kinds.add(isinstance(plan, RowPlan))
+        done += 1
+    assert done >= 12 and kinds == {True, False}
+
+
 def test_wide_target_and_mixed_cards():
     from continuousbayesiannetwork_b200 import synth
     from continuousbayesiannetwork_b200.engine import install_cpts
