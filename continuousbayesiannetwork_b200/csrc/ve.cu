@@ -122,6 +122,8 @@ struct cbn_ve_plan {
   int rows_n_inputs = 0, rows_n_steps = 0, rows_temp_floats = 0, rows_flags = 0;
   void* d_row_inputs = nullptr;
   void* d_row_steps = nullptr;
+  void* d_row_offsets = nullptr;
+  int rows_off_ints = 0;
   float* d_inter = nullptr;      // fused plans with identical indexing: targets interleaved [cfg][target][t]
   int interleaved = 0;           // number of targets stored in d_inter (0 = not interleaved)
   unsigned char* d_blob = nullptr;  // [GTable x n_tables][staged table pool]: one straight copy into shared memory
@@ -786,6 +788,7 @@ extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
   if (p->d_inter) cudaFree(p->d_inter);
   if (p->d_row_inputs) cudaFree(p->d_row_inputs);
   if (p->d_row_steps) cudaFree(p->d_row_steps);
+  if (p->d_row_offsets) cudaFree(p->d_row_offsets);
   delete p;
 }
 
@@ -992,6 +995,7 @@ struct RowInputDev {
 struct RowStepDev {
   const int* offsets;
   int out_size, sum_card, n_in, temp_off;
+  int off_at, pad;               // the step's offset table inside the plan's packed pool
   int in_id[CBN_MAX_CONTRACT_INPUTS];
   int sum_stride[CBN_MAX_CONTRACT_INPUTS];
 };
@@ -1005,32 +1009,105 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row.  Shared memory: [step descriptors][per warp: base offsets of the static inputs | temporaries].
+// One warp per row.  Shared memory: [step descriptors][input descriptors][offset tables][per warp: evidence codes of
+// the row | base offsets of the static inputs | temporaries].  Everything a step needs apart from the CPT slices
+// themselves (which stay in L1/L2) is read from shared memory; the inner loops are specialised on the number of factors
+// so their pointers and offsets live in registers and the loads of one output cell are independent of each other.
 // Linear mode rescales every temporary by its maximum (a per-row constant cancels in the final normalisation), so
 // products of hundreds of CPT entries neither underflow nor need log space; LOG mode keeps logs and uses log-sum-exp.
 template <bool LOG>
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  return (hi == NEG_INF) ? NEG_INF : hi + log1pf(expf(lo - hi));
+}
+
+template <bool LOG, int NIN>
+__device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* __restrict__ offs, const float* const* srcs, float* __restrict__ tout,
+                                               int lane) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float* src[NIN];
+  int ss[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) { src[k] = srcs[k]; ss[k] = S.sum_stride[k]; }
+  const int out_size = S.out_size, sum_card = S.sum_card;
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = lane; o < out_size; o += 32) {
+    const float* p[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) p[k] = src[k] + offs[k * out_size + o];
+    float acc = LOG ? NEG_INF : 0.0f;
+#pragma unroll 4
+    for (int sv = 0; sv < sum_card; ++sv) {
+      float prod = p[0][sv * ss[0]];
+#pragma unroll
+      for (int k = 1; k < NIN; ++k) {
+        const float x = p[k][sv * ss[k]];
+        prod = LOG ? prod + x : prod * x;
+      }
+      acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
+    }
+    tout[o] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  return mx;
+}
+
+template <bool LOG>
+__device__ __noinline__ float row_step_generic(const RowStepDev& S, const int* __restrict__ offs, const float* const* srcs, float* __restrict__ tout,
+                                               int lane) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = lane; o < S.out_size; o += 32) {
+    float acc = LOG ? NEG_INF : 0.0f;
+    for (int sv = 0; sv < S.sum_card; ++sv) {
+      float prod = LOG ? 0.0f : 1.0f;
+      for (int k = 0; k < S.n_in; ++k) {
+        const float x = srcs[k][offs[k * S.out_size + o] + sv * S.sum_stride[k]];
+        prod = LOG ? prod + x : prod * x;
+      }
+      acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
+    }
+    tout[o] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  return mx;
+}
+
+template <bool LOG>
 __global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
                                                            const RowStepDev* __restrict__ steps, int n_steps, int temp_floats,
+                                                           const int* __restrict__ off_pool, int off_ints, int n_evidence,
                                                            const uint8_t* __restrict__ ev, int64_t ld, int64_t n_rows,
                                                            int card_t, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowStepDev* sst = reinterpret_cast<RowStepDev*>(smem_raw);
+  RowInputDev* sin = reinterpret_cast<RowInputDev*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev));
+  int* soff = reinterpret_cast<int*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev) + size_t(n_inputs) * sizeof(RowInputDev));
   for (int i = threadIdx.x; i < n_steps * int(sizeof(RowStepDev) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(sst)[i] = reinterpret_cast<const uint32_t*>(steps)[i];
+  for (int i = threadIdx.x; i < n_inputs * int(sizeof(RowInputDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sin)[i] = reinterpret_cast<const uint32_t*>(inputs)[i];
+  for (int i = threadIdx.x; i < off_ints; i += blockDim.x) soff[i] = off_pool[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per_warp = ((n_inputs + 3) & ~3) + temp_floats;
-  int* base = reinterpret_cast<int*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev)) + size_t(warp) * per_warp;
-  float* temps = reinterpret_cast<float*>(base + ((n_inputs + 3) & ~3));
+  const int code_words = (n_evidence + 3) >> 2, base_words = (n_inputs + 3) & ~3;
+  const int per_warp = ((code_words + 3) & ~3) + base_words + temp_floats;
+  int* wmem = soff + ((off_ints + 3) & ~3) + size_t(warp) * per_warp;
+  uint8_t* codes = reinterpret_cast<uint8_t*>(wmem);
+  int* base = wmem + ((code_words + 3) & ~3);
+  float* temps = reinterpret_cast<float*>(base + base_words);
   const float NEG_INF = __int_as_float(0xff800000);
   for (int64_t row = int64_t(blockIdx.x) * ROWS_WARPS + warp; row < n_rows; row += int64_t(gridDim.x) * ROWS_WARPS) {
-    // slice every static input by this row's evidence codes
+    // the row's evidence codes (one byte per evidence column), then the slice offset of every static input
+    for (int e = lane; e < n_evidence; e += 32) codes[e] = ev[int64_t(e) * ld + row];
+    __syncwarp();
     bool bad = false;
     for (int k = lane; k < n_inputs; k += 32) {
-      const RowInputDev& I = inputs[k];
+      const RowInputDev& I = sin[k];
       int b = 0;
       for (int j = 0; j < I.n_ev; ++j) {
-        const int c = ev[int64_t(I.slot[j]) * ld + row];
+        const int c = codes[I.slot[j]];
         bad |= (c == CBN_UNSEEN);
         b += c * I.stride[j];
       }
@@ -1042,26 +1119,21 @@ __global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __
       for (int j = 0; j < n_steps; ++j) {
         const RowStepDev& S = sst[j];
         float* tout = temps + S.temp_off;
-        float mx = LOG ? NEG_INF : 0.0f;
-        for (int o = lane; o < S.out_size; o += 32) {
-          float acc = LOG ? NEG_INF : 0.0f;
-          for (int sv = 0; sv < S.sum_card; ++sv) {
-            float prod = LOG ? 0.0f : 1.0f;
-            for (int k = 0; k < S.n_in; ++k) {
-              const int id = S.in_id[k];
-              const float* src = id < n_inputs ? inputs[id].data + base[id] : temps + sst[id - n_inputs].temp_off;
-              const float x = src[__ldg(S.offsets + k * S.out_size + o) + sv * S.sum_stride[k]];
-              prod = LOG ? prod + x : prod * x;
-            }
-            if (LOG) {
-              const float hi = fmaxf(acc, prod), lo = fminf(acc, prod);
-              acc = (hi == NEG_INF) ? NEG_INF : hi + log1pf(expf(lo - hi));
-            } else {
-              acc += prod;
-            }
+        const int* offs = soff + S.off_at;
+        const float* srcs[CBN_MAX_CONTRACT_INPUTS];
+#pragma unroll
+        for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+          if (k < S.n_in) {
+            const int id = S.in_id[k];
+            srcs[k] = id < n_inputs ? sin[id].data + base[id] : temps + sst[id - n_inputs].temp_off;
           }
-          tout[o] = acc;
-          mx = fmaxf(mx, acc);
+        float mx;
+        switch (S.n_in) {
+          case 1: mx = row_step_body<LOG, 1>(S, offs, srcs, tout, lane); break;
+          case 2: mx = row_step_body<LOG, 2>(S, offs, srcs, tout, lane); break;
+          case 3: mx = row_step_body<LOG, 3>(S, offs, srcs, tout, lane); break;
+          case 4: mx = row_step_body<LOG, 4>(S, offs, srcs, tout, lane); break;
+          default: mx = row_step_generic<LOG>(S, offs, srcs, tout, lane); break;
         }
         mx = warp_max(mx);
         __syncwarp();
@@ -1128,6 +1200,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   }
   std::vector<RowStepDev> hs(n_steps);
   int temp = 0;
+  long long off_ints = 0;
   for (int j = 0; j < n_steps; ++j) {
     const cbn_row_step& S = steps[j];
     if (S.out_size < 1 || S.sum_card < 1 || S.n_in < 1 || S.n_in > CBN_MAX_CONTRACT_INPUTS || !S.offsets)
@@ -1135,6 +1208,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
     hs[j] = RowStepDev{};
     hs[j].offsets = S.offsets; hs[j].out_size = S.out_size; hs[j].sum_card = S.sum_card; hs[j].n_in = S.n_in;
     hs[j].temp_off = temp;
+    hs[j].off_at = (int)off_ints;
     for (int k = 0; k < S.n_in; ++k) {
       if (S.in_id[k] < 0 || S.in_id[k] >= n_inputs + j)
         return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: input %d refers to a later step", j, k);
@@ -1142,10 +1216,14 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
       hs[j].sum_stride[k] = S.sum_stride[k];
     }
     temp += (S.out_size + 3) & ~3;
+    off_ints += (long long)S.n_in * S.out_size;
   }
   if (steps[n_steps - 1].out_size != card_t)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: the last step must produce card_t cells");
-  const size_t smem = size_t(n_steps) * sizeof(RowStepDev) + size_t(ROWS_WARPS) * (((n_inputs + 3) & ~3) + temp) * 4;
+  const size_t code_words = ((size_t(n_evidence) + 3) / 4 + 3) & ~size_t(3);
+  const size_t per_warp = code_words + ((n_inputs + 3) & ~3) + temp;
+  const size_t smem = size_t(n_steps) * sizeof(RowStepDev) + size_t(n_inputs) * sizeof(RowInputDev) +
+                      size_t((off_ints + 3) & ~3ll) * 4 + size_t(ROWS_WARPS) * per_warp * 4;
   if (smem > 200 * 1024)
     return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "per-row plan needs %zu bytes of shared memory per CTA (limit 200 KB)", smem);
   cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
@@ -1153,11 +1231,16 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   p->device = ctx->device; p->kind = 1; p->n_evidence = n_evidence; p->card_t = card_t; p->n_out = 1; p->normalize_mask = 1;
   p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
   p->rows_n_inputs = n_inputs; p->rows_n_steps = n_steps; p->rows_temp_floats = temp; p->rows_flags = flags;
+  p->rows_off_ints = (int)off_ints;
   p->blob_bytes = smem;
   cudaError_t e = cudaMalloc(&p->d_row_inputs, sizeof(RowInputDev) * n_inputs);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_row_inputs, hi.data(), sizeof(RowInputDev) * n_inputs, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_row_steps, sizeof(RowStepDev) * n_steps);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_row_steps, hs.data(), sizeof(RowStepDev) * n_steps, cudaMemcpyHostToDevice);
+  // the steps' offset tables, packed into one pool that the kernel stages in shared memory
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_row_offsets, size_t(std::max<long long>(off_ints, 1)) * 4);
+  for (int j = 0; e == cudaSuccess && j < n_steps; ++j)
+    e = cudaMemcpy((int*)p->d_row_offsets + hs[j].off_at, steps[j].offsets, size_t(steps[j].n_in) * steps[j].out_size * 4, cudaMemcpyDeviceToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) { cbn_ve_plan_destroy(p); return cbn_fail(ctx, CBN_ERR_CUDA, "per-row plan upload: %s", cudaGetErrorString(e)); }
@@ -1171,10 +1254,12 @@ static int ve_run_rows(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, in
   if (p->rows_flags & CBN_ROWS_LOG_SPACE)
     ve_rows_kernel<true><<<blocks, ROWS_TPB, p->blob_bytes, s>>>((const RowInputDev*)p->d_row_inputs, p->rows_n_inputs,
                                                                 (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+                                                                (const int*)p->d_row_offsets, p->rows_off_ints, p->n_evidence,
                                                                 ev, ld, n_rows, p->card_t, out);
   else
     ve_rows_kernel<false><<<blocks, ROWS_TPB, p->blob_bytes, s>>>((const RowInputDev*)p->d_row_inputs, p->rows_n_inputs,
                                                                  (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+                                                                 (const int*)p->d_row_offsets, p->rows_off_ints, p->n_evidence,
                                                                  ev, ld, n_rows, p->card_t, out);
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
@@ -1283,7 +1368,9 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     if (!posteriors_host[o]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: posterior %d is NULL", o);
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
-  const int64_t chunk = 1 << 20;  // rows per chunk
+  // rows per chunk: small enough that the H2D copy of chunk k+1 hides behind the (much larger) D2H copy of chunk k even
+  // for a 1M-row call, large enough that the per-chunk launch and copy-call overhead stays below a few percent
+  const int64_t chunk = 1 << 18;
   const int ne = std::max(plan->n_evidence, 1);
   const size_t out_stride = size_t(chunk) * ct;   // floats per output inside a staging buffer
   int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float));
