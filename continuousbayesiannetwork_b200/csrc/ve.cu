@@ -896,7 +896,7 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
 }
 
 // large batches go through the tile-staged kernel (CBN_GATHER_TILES=0/1 forces the choice; default: >= 2^22 rows)
-bool use_tiles(const cbn_ve_plan* p, int64_t n_rows) {
+bool use_tiles(const cbn_ve_plan* p, int64_t n_rows, bool force = false) {
   static int mode = -2;
   if (mode == -2) { const char* e = getenv("CBN_GATHER_TILES"); mode = e ? atoi(e) : -1; }
   if (mode == 0 || p->card_t > GATHER_MAX_CT || p->n_evidence < 1) return false;
@@ -907,12 +907,12 @@ bool use_tiles(const cbn_ve_plan* p, int64_t n_rows) {
       if (!seen[t.slot[j]]) { seen[t.slot[j]] = 1; ++n; }
   if (n < 1 || n > GT_MAX_COLS) return false;
   if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS > 150 * 1024) return false;
-  return mode == 1 || n_rows >= (int64_t(1) << 22);
+  return force || mode == 1 || n_rows >= (int64_t(1) << 22);
 }
 
 int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
-                      const GatherOuts& outs, cudaStream_t s) {
-  const bool tiles = use_tiles(plan, n_rows);
+                      const GatherOuts& outs, cudaStream_t s, bool force_tiles = false) {
+  const bool tiles = use_tiles(plan, n_rows, force_tiles);
   if (plan->interleaved) {
     const int key = plan->card_t * 10 + plan->interleaved;
     if (tiles) switch (key) {
@@ -1368,9 +1368,11 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     if (!posteriors_host[o]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: posterior %d is NULL", o);
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
-  // rows per chunk: small enough that the H2D copy of chunk k+1 hides behind the (much larger) D2H copy of chunk k even
-  // for a 1M-row call, large enough that the per-chunk launch and copy-call overhead stays below a few percent
-  const int64_t chunk = 1 << 18;
+  // rows per chunk: half the call (so the H2D copy and the kernel of the second half hide behind the D2H copy of the
+  // first), between 256K and 1M rows -- PCIe copies below ~4 MB lose bandwidth to per-copy overhead (52 vs 57 GB/s
+  // measured), chunks above 1M rows only add start-up latency.  Mapped (zero-copy) access from the kernel was measured
+  // slower than the copy engines in both directions (45 GB/s stores; tools/exp_e2e.py) and is not used.
+  const int64_t chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 18, ((n_rows / 2 + 65535) >> 16) << 16));
   const int ne = std::max(plan->n_evidence, 1);
   const size_t out_stride = size_t(chunk) * ct;   // floats per output inside a staging buffer
   int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float));
@@ -1398,16 +1400,16 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
       pending_row[b] = -1;
     }
     uint8_t* din = (uint8_t*)ctx->io_dev_in[b];
-    for (int e = 0; e < plan->n_evidence; ++e) {
-      const uint8_t* src = ev_codes_host + int64_t(e) * ld + r0;
-      if (in_pinned) {
-        CBN_CUDA(ctx, cudaMemcpyAsync(din + int64_t(e) * chunk, src, m, cudaMemcpyHostToDevice, s));
+    if (plan->n_evidence > 0) {
+      if (in_pinned) {   // one strided copy for all columns of the chunk
+        CBN_CUDA(ctx, cudaMemcpy2DAsync(din, size_t(chunk), ev_codes_host + r0, size_t(ld), size_t(m), size_t(plan->n_evidence),
+                                        cudaMemcpyHostToDevice, s));
       } else {
-        memcpy((uint8_t*)ctx->io_pin_in[b] + int64_t(e) * chunk, src, m);
+        for (int e = 0; e < plan->n_evidence; ++e)
+          memcpy((uint8_t*)ctx->io_pin_in[b] + int64_t(e) * chunk, ev_codes_host + int64_t(e) * ld + r0, m);
+        CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], size_t(chunk) * plan->n_evidence, cudaMemcpyHostToDevice, s));
       }
     }
-    if (!in_pinned && plan->n_evidence > 0)
-      CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], size_t(chunk) * plan->n_evidence, cudaMemcpyHostToDevice, s));
     GatherOuts go{};
     for (int o = 0; o < n_out; ++o) go.out[o] = (float*)ctx->io_dev_out[b] + o * out_stride;
     go.normalize_mask = plan->normalize_mask;
