@@ -324,6 +324,21 @@ def run_ours(args):
     queries_per_step = rows * len(ASIA_TARGETS) * world
     value = queries_per_step * args.steps / q_s
     launches = args.steps * world
+    # the same steps strictly one after the other on ONE stream (no overlap between consecutive launches): what a single
+    # launch costs including its launch latency; reported beside the overlapped figure
+    def serial_steps(first, count):
+        for i in range(first, first + count):
+            slot_graphs[i % ring].replay()
+
+    serial_steps(0, args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    serial_steps(args.warmup, args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    serial_s = max_over_ranks(e0.elapsed_time(e1)) / 1e3
+    barrier()
     # roofline of the dominant kernel (fused gather): algorithmic bytes = relevant evidence codes in (once) +
     # one fp32 posterior per target out
     alg_bytes = rows * fused.algorithmic_bytes_per_row()
@@ -399,7 +414,10 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": _profile_traffic("gather_inter_kernel<2,3>"), "kernel": "gather_inter_kernel<2,3> (3 binary targets fused, interleaved table)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src},
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src,
+                         "one_stream": {"launch_us": serial_s / args.steps * 1e6, "achieved": alg_bytes / (serial_s / args.steps) / 1e9,
+                                        "frac": alg_bytes / (serial_s / args.steps) / 1e9 / peak_gbs,
+                                        "note": "same launches back to back on one stream: includes the launch gap the 3-stream graph hides"}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "fit": {"metric": "CPT-fit samples/sec", "value": fit_rate, "unit": "samples/s", "n_samples_per_gpu_per_step": n_big,

@@ -752,7 +752,9 @@ extern "C" int cbn_count_plan_updates_per_sample(const cbn_count_plan* plan) { r
 extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
                              unsigned long long* counts, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run: ctx is NULL");
-  if (!plan || !codes || !counts || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
+  if (!plan || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
+  if (n == 0) return CBN_OK;                 // nothing to count (an empty torch tensor has a NULL data pointer)
+  if (!codes || !counts) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: bad argument");
   if (ld < n || (ld % 16) != 0 || !is_aligned(codes, 16))
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: code matrix needs ld >= n, ld %% 16 == 0 and a 16-byte aligned base (ld=%lld, n=%lld)",
                     (long long)ld, (long long)n);

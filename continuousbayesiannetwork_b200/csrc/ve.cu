@@ -964,8 +964,9 @@ int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_c
 
 int check_run_args(cbn_ctx* ctx, const char* fn, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
                    float* const* posteriors, GatherOuts* outs) {
-  if (!plan || !posteriors || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes))
-    return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
+  if (!plan || n_rows < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
+  if (n_rows == 0) return CBN_OK;            // an empty batch has no buffers to check (torch gives NULL for empty tensors)
+  if (!posteriors || (plan->n_evidence > 0 && !ev_codes)) return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
   if (plan->n_evidence > 0 && (ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
     return cbn_fail(ctx, CBN_ERR_INVALID, "%s: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base", fn);
   outs->normalize_mask = plan->normalize_mask;
@@ -1294,7 +1295,9 @@ extern "C" int cbn_ve_run_codes_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, con
 extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols,
                               const float* const* domains, int64_t n_rows, float* posterior, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_f32: ctx is NULL");
-  if (!plan || !posterior || n_rows < 0 || (plan->n_evidence > 0 && (!ev_cols || !domains)))
+  if (!plan || n_rows < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: bad argument");
+  if (n_rows == 0) return CBN_OK;
+  if (!posterior || (plan->n_evidence > 0 && (!ev_cols || !domains)))
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: bad argument");
   if (plan->n_out != 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32: fused plans take codes (cbn_ve_run_codes_multi)");
   if (plan->kind != 0) return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32: per-row plans take codes (encode with cbn_encode_f32)");
@@ -1360,7 +1363,9 @@ static int ensure_io(cbn_ctx* ctx, size_t in_bytes, size_t out_bytes) {
 extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
                                            int64_t n_rows, float* const* posteriors_host) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
-  if (!plan || !posteriors_host || n_rows < 0 || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
+  if (!plan || n_rows < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
+  if (n_rows == 0) return CBN_OK;
+  if (!posteriors_host || (plan->n_evidence > 0 && !ev_codes_host) || ld < n_rows)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
   if (plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: per-row plans are device-side only");
   const int n_out = plan->n_out, ct = plan->card_t;

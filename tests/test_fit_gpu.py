@@ -204,6 +204,29 @@ def test_unseen_codes_are_skipped_not_corrupting():
     assert t.table_view(t.counts, "b").cpu().tolist() == [[1, 1], [1, 1], [0, 1]]
 
 
+@pytest.mark.parametrize("net", ["asia", "alarm", "ktree"])
+def test_unseen_codes_in_the_tile_kernel_skip_only_their_families(net):
+    """CBN_UNSEEN codes scattered through a large batch (tile kernel with merged tables, exact scalar path) plus a
+    ragged tail (direct kernel): a sample is skipped only for the families that contain the unseen variable."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+    from oracle.build_oracle import count_families
+
+    spec = {"asia": synth.asia, "alarm": synth.alarm, "ktree": lambda: synth.random_ktree_dag(n=60, seed=3)}[net]()
+    n = 300_001
+    codes = sample_network(spec, seed=13, first=0, n=n, device=DEV)
+    g = torch.Generator(device=DEV); g.manual_seed(2)
+    hit = torch.rand(codes.shape, device=DEV, generator=g) < 1e-3
+    codes[hit] = 255
+    t = tables_from_spec(spec, DEV)
+    t.count(codes, n)
+    fams = [spec.parents[i] + [i] for i in range(spec.n)]
+    want = count_families(codes.cpu().numpy(), n, fams, spec.cards)
+    for i, name in enumerate(spec.names):
+        assert np.array_equal(t.table_view(t.counts, name).cpu().numpy(), want[i]), name
+    assert int(t.table_view(t.counts, spec.names[0]).sum()) < n
+
+
 def test_sample_count_lives_on_the_device_next_to_the_tables():
     """Sharded fits all-reduce tables and sample count in one buffer; the normalisation reads the count on the device.
     Single process here: the buffer layout, the lazy host view and accumulation over calls."""

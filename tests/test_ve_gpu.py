@@ -133,6 +133,31 @@ def test_config5_layered_dag_shallow_patterns():
     assert done >= 12 and kinds == {True, False}
 
 
+def test_empty_and_tiny_batches():
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.asia()
+    _, infer = install_cpts(spec, DEV)
+    names = ["asia", "smoke", "xray", "dysp"]
+    ids = [spec.names.index(e) for e in names]
+    plan = infer.plan("lung", names)
+    fused = infer.fused_plan(["lung", "tub", "bronc"], names)
+    empty = torch.zeros((4, 16), dtype=torch.uint8, device=DEV)
+    assert tuple(plan.run_codes(empty, 0).shape) == (0, 2)
+    assert all(tuple(o.shape) == (0, 2) for o in fused.run_codes(empty, 0))
+    assert tuple(plan.run_codes_host(empty.cpu(), 0, torch.empty((0, 2), dtype=torch.float32)).shape) == (0, 2)
+    codes = synth.sample_forward_numpy(spec, 77, 0, 7)
+    for n in (1, 2, 3, 5, 7):
+        ev = codes[ids][:, :n].T
+        got = plan.run_codes(_codes_matrix(ev), n).cpu().numpy()
+        want = O.ve_posterior(_net(spec), spec.names.index("lung"), ids, ev)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+        host = torch.full((n + 1, 2), -1.0, dtype=torch.float32)
+        plan.run_codes_host(_codes_matrix(ev).cpu(), n, host)
+        assert np.array_equal(host[:n].numpy(), got) and bool((host[n] == -1).all())     # nothing written past n rows
+
+
 def test_wide_target_and_mixed_cards():
     from continuousbayesiannetwork_b200 import synth
     from continuousbayesiannetwork_b200.engine import install_cpts
