@@ -181,6 +181,19 @@ class BayesianNetwork:
         assert pdf.shape == domains.shape, "pdf and domain must have same shape."
         return pdf, domains
 
+    def infer_many(self, target_nodes: List[str], evidence: Dict[str, torch.Tensor] = None) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        """``infer`` for several targets under the same evidence in one pass (evidence uploaded and encoded once,
+        equal-cardinality targets answered by one fused launch).  Returns name -> (pdf, domains) as ``infer`` does."""
+        for tn in target_nodes:
+            if tn not in self.nodes_obj:
+                raise ValueError(f"{tn} is not a node of the network")
+        pdfs = self.inference_obj.infer_many(list(target_nodes), evidence or {})
+        out = {}
+        for tn, pdf in pdfs.items():
+            dom = self.tables.domains[self.tables.index[tn]]
+            out[tn] = (pdf, dom.unsqueeze(0).expand(pdf.shape[0], -1))
+        return out
+
     def infer_map(self, target_node: str, evidence: Dict[str, torch.Tensor]) -> torch.Tensor:
         """MAP value of the target per row (what ``benchmarking_df`` extracts, :357-366)."""
         pdf, dom = self.infer(target_node, evidence, N_max=1 << 30)

@@ -14,6 +14,7 @@ class ExactInference(BaseInference):
         super(ExactInference, self).__init__(config=config, **kwargs)
         self.normalization = "row"
         self.compiler: Optional[VECompiler] = None
+        self._fused: Dict[tuple, FusedPlan] = {}
         self._setup_model(config, **kwargs)
 
     def _setup_model(self, config: Dict, **kwargs):
@@ -29,6 +30,7 @@ class ExactInference(BaseInference):
         """Attach the fitted network tables (called by BayesianNetwork after every fit)."""
         self.tables = tables
         self.compiler = VECompiler(tables, **self._budget)
+        self._fused: Dict[tuple, FusedPlan] = {}
 
     def plan(self, target_node: str, evidence_names: Sequence[str], do: Sequence[str] = ()) -> QueryPlan:
         assert self.compiler is not None, "inference engine is not bound to a fitted network"
@@ -37,6 +39,45 @@ class ExactInference(BaseInference):
     def fused_plan(self, targets: Sequence[str], evidence_names: Sequence[str]) -> FusedPlan:
         """One launch for several targets that share the evidence list (same target cardinality)."""
         return FusedPlan([self.plan(t, evidence_names) for t in targets])
+
+    def infer_many(self, targets: Sequence[str], evidence: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Posteriors of SEVERAL targets under the same evidence: the evidence columns are uploaded and encoded once,
+        and targets of equal cardinality are answered by one fused launch (``cbn_ve_plan_fuse``).  Not part of the
+        reference's surface (its ``infer`` takes one target per call); row-normalised posteriors, float32
+        [n_queries, card(target)] on the device, keyed by target name."""
+        t = self.tables
+        evidence = evidence or {}
+        names = [n for n in evidence.keys() if n not in targets]
+        for n in list(names) + list(targets):
+            if n not in t.index:
+                raise ValueError(f"{n} is not a node of the network")
+        nq = int(evidence[names[0]].shape[0]) if names else 1
+        ld = (max(nq, 1) + 15) // 16 * 16
+        codes = torch.empty((max(len(names), 1), ld), dtype=torch.uint8, device=t.device)
+        for e, n in enumerate(names):
+            c = evidence[n]
+            if c.shape[0] != nq:
+                raise ValueError("n_queries must be equal for all features.")
+            t.encode(c.to(t.device, torch.float32, non_blocking=True).reshape(-1), t.index[n], codes[e])
+        out: Dict[str, torch.Tensor] = {}
+        by_card: Dict[int, list] = {}
+        for tg in targets:
+            by_card.setdefault(t.cards[t.index[tg]], []).append(tg)
+        for _, group in by_card.items():
+            plans = [self.plan(tg, names) for tg in group]
+            fusable = len(group) > 1 and all(isinstance(p, QueryPlan) for p in plans)
+            for i in range(0, len(group), 8 if fusable else 1):
+                chunk = group[i: i + 8]
+                if fusable and len(chunk) > 1:
+                    key = ("fused", tuple(chunk), tuple(names))
+                    fused = self._fused.get(key)
+                    if fused is None:
+                        fused = self._fused[key] = FusedPlan(plans[i: i + 8])
+                    for tg, o in zip(chunk, fused.run_codes(codes, nq)):
+                        out[tg] = o
+                else:
+                    out[chunk[0]] = plans[i].run_codes(codes, nq)
+        return out
 
     def _infer(self, target_node: str, evidence: Dict[str, torch.Tensor], do=None, **kwargs) -> torch.Tensor:
         """Posterior ``P(target | evidence)`` per row: float32 [n_queries, card(target)] on the device.
