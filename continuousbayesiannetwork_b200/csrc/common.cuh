@@ -22,7 +22,15 @@ struct cbn_ctx {
   void* io_pin_in[2] = {nullptr, nullptr};
   void* io_pin_out[2] = {nullptr, nullptr};
   size_t io_in_bytes = 0, io_out_bytes = 0;
+  // private stream-ordered pool for small per-call scratch; it keeps its memory across synchronisations (the default
+  // pool hands memory back to the driver at every sync, which turns each scratch allocation into a millisecond)
+  cudaMemPool_t pool = nullptr;
 };
+
+// stream-ordered scratch allocation from the context's pool
+static inline cudaError_t cbn_scratch_alloc(cbn_ctx* ctx, void** ptr, size_t bytes, cudaStream_t s) {
+  return ctx->pool ? cudaMallocFromPoolAsync(ptr, bytes, ctx->pool, s) : cudaMallocAsync(ptr, bytes, s);
+}
 
 extern thread_local std::string cbn_tls_error;
 

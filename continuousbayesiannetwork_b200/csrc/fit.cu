@@ -37,6 +37,20 @@ extern "C" int cbn_ctx_create(int device, cbn_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  {
+    cudaMemPoolProps pp = {};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &pp) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      ctx->pool = nullptr;          // fall back to the default pool
+      cudaGetLastError();
+    }
+  }
   *out = ctx;
   return CBN_OK;
 }
@@ -52,6 +66,7 @@ extern "C" void cbn_ctx_destroy(cbn_ctx* ctx) {
     if (ctx->io_pin_in[i]) cudaFreeHost(ctx->io_pin_in[i]);
     if (ctx->io_pin_out[i]) cudaFreeHost(ctx->io_pin_out[i]);
   }
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 
@@ -99,6 +114,20 @@ __global__ void domain_init_kernel(uint32_t* gset, int* overflow) {
   if (threadIdx.x == 0) *overflow = 0;
 }
 
+__device__ __forceinline__ bool domain_note(uint32_t* sset, uint32_t b, uint32_t& last, int* overflow) {
+  if (b == last) return true;   // runs of equal values are the common case
+  last = b;
+  const uint32_t h = hash32(b) & (DOM_SLOTS - 1);
+  if (sset[h] == b) return true;   // fast path: already present at its home slot
+  if (!set_insert(sset, b)) {
+    atomicExch(overflow, 1);       // more than DOM_SLOTS distinct values: not a discrete column
+    return false;
+  }
+  return true;
+}
+
+// 128-bit loads, four values per thread and iteration (the column base is 16-byte aligned when VEC)
+template <bool VEC>
 __global__ void __launch_bounds__(256) domain_scan_kernel(const float* __restrict__ col, int64_t n,
                                                           uint32_t* gset, int* overflow) {
   __shared__ uint32_t sset[DOM_SLOTS];
@@ -106,18 +135,24 @@ __global__ void __launch_bounds__(256) domain_scan_kernel(const float* __restric
   __syncthreads();
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   uint32_t last = DOM_EMPTY;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t b = canon_bits(__ldg(col + i));
-    if (b == last) continue;  // runs of equal values are the common case
-    last = b;
-    // fast path: already present
-    uint32_t h = hash32(b) & (DOM_SLOTS - 1);
-    if (sset[h] == b) continue;
-    if (!set_insert(sset, b)) {
-      atomicExch(overflow, 1);   // more than DOM_SLOTS distinct values: not a discrete column, stop early
-      break;
+  bool ok = true;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4 && ok; i += 2 * stride) {
+      const float4 a = ld_nc_f128(reinterpret_cast<const float4*>(col) + i);
+      const bool two = i + stride < n4;
+      float4 c = a;
+      if (two) c = ld_nc_f128(reinterpret_cast<const float4*>(col) + i + stride);
+      ok = domain_note(sset, canon_bits(a.x), last, overflow) && domain_note(sset, canon_bits(a.y), last, overflow) &&
+           domain_note(sset, canon_bits(a.z), last, overflow) && domain_note(sset, canon_bits(a.w), last, overflow) &&
+           domain_note(sset, canon_bits(c.x), last, overflow) && domain_note(sset, canon_bits(c.y), last, overflow) &&
+           domain_note(sset, canon_bits(c.z), last, overflow) && domain_note(sset, canon_bits(c.w), last, overflow);
     }
-    if (*reinterpret_cast<volatile int*>(overflow)) break;
+    for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n && ok; i += stride)
+      ok = domain_note(sset, canon_bits(__ldg(col + i)), last, overflow);
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n && ok; i += stride)
+      ok = domain_note(sset, canon_bits(__ldg(col + i)), last, overflow);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) {
@@ -169,12 +204,13 @@ extern "C" int cbn_domain_f32(cbn_ctx* ctx, const float* col, int64_t n, float* 
   DeviceGuard g(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   uint32_t* gset = nullptr;
-  CBN_CUDA(ctx, cudaMallocAsync((void**)&gset, (DOM_SLOTS + 1) * sizeof(uint32_t), s));
+  CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&gset, (DOM_SLOTS + 1) * sizeof(uint32_t), s));
   int* overflow = reinterpret_cast<int*>(gset + DOM_SLOTS);
   domain_init_kernel<<<1, 256, 0, s>>>(gset, overflow);
   if (n > 0) {
     int blocks = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), int64_t(ctx->sm_count) * 8);
-    domain_scan_kernel<<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
+    if (is_aligned(col, 16)) domain_scan_kernel<true><<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
+    else domain_scan_kernel<false><<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
   }
   domain_finish_kernel<<<1, DOM_SLOTS, 0, s>>>(gset, overflow, domain_out, card_out);
   CBN_CHECK_LAUNCH(ctx);
@@ -286,7 +322,7 @@ extern "C" int cbn_cpt_from_counts(cbn_ctx* ctx, const long long* counts, const 
     max_rows = std::max(max_rows, h[f].n_rows);
   }
   CptFam* d = nullptr;
-  CBN_CUDA(ctx, cudaMallocAsync((void**)&d, sizeof(CptFam) * n_fams, s));
+  CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&d, sizeof(CptFam) * n_fams, s));
   CBN_CUDA(ctx, cudaMemcpyAsync(d, h.data(), sizeof(CptFam) * n_fams, cudaMemcpyHostToDevice, s));
   // pageable source: the copy above is staged before the call returns, h may go out of scope
   for (int f0 = 0; f0 < n_fams; f0 += 65535) {
@@ -538,7 +574,7 @@ extern "C" int cbn_sample_forward(cbn_ctx* ctx, int32_t n_vars, const int32_t* o
     }
   }
   SampleFam* d = nullptr;
-  CBN_CUDA(ctx, cudaMallocAsync((void**)&d, sizeof(SampleFam) * n_vars, s));
+  CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&d, sizeof(SampleFam) * n_vars, s));
   CBN_CUDA(ctx, cudaMemcpyAsync(d, h.data(), sizeof(SampleFam) * n_vars, cudaMemcpyHostToDevice, s));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8);
   sample_forward_kernel<<<blocks, 256, 0, s>>>(n_vars, d, cdf, seed, first_sample, n, codes, ld);

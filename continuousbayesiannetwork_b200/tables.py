@@ -145,6 +145,25 @@ class DiscreteTables:
                 "brute-force estimator")
         return dom[:c].clone()
 
+    def discover_domains(self, cols: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """``discover_domain`` for many columns with ONE host synchronisation (all scans are enqueued first)."""
+        k = len(cols)
+        dom = torch.empty((k, 256), dtype=torch.float32, device=self.device)
+        card = torch.empty(k, dtype=torch.int32, device=self.device)
+        keep = []
+        for i, col in enumerate(cols):
+            col = col.to(self.device, torch.float32).contiguous()
+            keep.append(col)
+            N.check(N.lib().cbn_domain_f32(self.ctx.handle, col.data_ptr(), col.numel(), dom[i].data_ptr(), card[i:].data_ptr(),
+                                           N.stream_ptr(self.device)), self.ctx.handle)
+        cards = card.cpu().tolist()
+        for i, c in enumerate(cards):
+            if c < 0:
+                raise ValueError(
+                    f"column {i} has more than {N.MAX_CARD} distinct values; it is not a discrete variable for the "
+                    "brute-force estimator")
+        return [dom[i, :c].clone() for i, c in enumerate(cards)]
+
     def encode(self, col: torch.Tensor, var: int, out: torch.Tensor, unseen: Optional[torch.Tensor] = None):
         col = col.to(self.device, torch.float32).contiguous()
         N.check(N.lib().cbn_encode_f32(self.ctx.handle, col.data_ptr(), col.numel(), self.domains[var].data_ptr(),
@@ -214,8 +233,7 @@ class DiscreteTables:
 
     def fit_columns(self, cols: Dict[str, torch.Tensor]):
         """Full fit from float32 columns: domains, codes, counts, CPTs."""
-        doms = [self.discover_domain(cols[n].reshape(-1)) for n in self.names]
-        self.set_domains(doms)
+        self.set_domains(self.discover_domains([cols[n].reshape(-1) for n in self.names]))
         codes = self.encode_columns(cols)
         n = int(next(iter(cols.values())).numel())
         self.count(codes, n)
