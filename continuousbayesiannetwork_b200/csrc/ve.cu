@@ -1033,7 +1033,29 @@ __device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* _
   for (int k = 0; k < NIN; ++k) { src[k] = srcs[k]; ss[k] = S.sum_stride[k]; }
   const int out_size = S.out_size, sum_card = S.sum_card;
   float mx = LOG ? NEG_INF : 0.0f;
-  for (int o = lane; o < out_size; o += 32) {
+  int o = lane;
+  // two output cells per lane and iteration: their loads are independent, which doubles the memory-level parallelism
+  for (; o + 32 < out_size; o += 64) {
+    const float *p0[NIN], *p1[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) { p0[k] = src[k] + offs[k * out_size + o]; p1[k] = src[k] + offs[k * out_size + o + 32]; }
+    float a0 = LOG ? NEG_INF : 0.0f, a1 = a0;
+#pragma unroll 2
+    for (int sv = 0; sv < sum_card; ++sv) {
+      float q0 = p0[0][sv * ss[0]], q1 = p1[0][sv * ss[0]];
+#pragma unroll
+      for (int k = 1; k < NIN; ++k) {
+        const float x0 = p0[k][sv * ss[k]], x1 = p1[k][sv * ss[k]];
+        q0 = LOG ? q0 + x0 : q0 * x0;
+        q1 = LOG ? q1 + x1 : q1 * x1;
+      }
+      a0 = LOG ? lse2<LOG>(a0, q0) : a0 + q0;
+      a1 = LOG ? lse2<LOG>(a1, q1) : a1 + q1;
+    }
+    tout[o] = a0; tout[o + 32] = a1;
+    mx = fmaxf(mx, fmaxf(a0, a1));
+  }
+  for (; o < out_size; o += 32) {
     const float* p[NIN];
 #pragma unroll
     for (int k = 0; k < NIN; ++k) p[k] = src[k] + offs[k * out_size + o];
