@@ -895,7 +895,7 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   return CBN_OK;
 }
 
-// large batches go through the tile-staged kernel (CBN_GATHER_TILES=0/1 forces the choice; default: >= 2^22 rows)
+// large batches go through the tile-staged kernel (CBN_GATHER_TILES=0/1 forces the choice; default: >= 2^21 rows)
 bool use_tiles(const cbn_ve_plan* p, int64_t n_rows, bool force = false) {
   static int mode = -2;
   if (mode == -2) { const char* e = getenv("CBN_GATHER_TILES"); mode = e ? atoi(e) : -1; }
@@ -907,7 +907,7 @@ bool use_tiles(const cbn_ve_plan* p, int64_t n_rows, bool force = false) {
       if (!seen[t.slot[j]]) { seen[t.slot[j]] = 1; ++n; }
   if (n < 1 || n > GT_MAX_COLS) return false;
   if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS > 150 * 1024) return false;
-  return force || mode == 1 || n_rows >= (int64_t(1) << 22);
+  return force || mode == 1 || n_rows >= (int64_t(1) << 21);
 }
 
 int ve_run_codes_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,

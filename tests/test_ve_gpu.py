@@ -284,7 +284,7 @@ def test_fused_multi_target_launch_matches_single_plans():
 
 
 def test_tile_staged_kernel_matches_direct_kernel_on_large_batches():
-    """Batches of >= 2^22 rows run through the tile-staged kernel (bulk async copies of the evidence tiles); the
+    """Batches of >= 2^21 rows run through the tile-staged kernel (bulk async copies of the evidence tiles); the
     same rows answered in smaller calls use the direct kernel: the posteriors must be bit-identical, including the
     ragged last tile, an unseen code and a slice of the batch checked against the oracle."""
     from continuousbayesiannetwork_b200 import synth
@@ -299,7 +299,7 @@ def test_tile_staged_kernel_matches_direct_kernel_on_large_batches():
     ev[n - 2, 4] = 255
     ev[12345, 0] = 255
     m = _codes_matrix(ev)
-    half = 1 << 21
+    half = 1 << 20
     for plan in (infer.fused_plan(synth.ALARM_TARGETS, synth.ALARM_EVIDENCE), infer.plan("VENTLUNG", synth.ALARM_EVIDENCE),
                  infer.plan("LVFAILURE", synth.ALARM_EVIDENCE[:5])):
         multi = hasattr(plan, "n_out")
