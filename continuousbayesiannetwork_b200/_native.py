@@ -96,6 +96,8 @@ SIGNATURES = {
     "cbn_device_sm_count": (C.c_int, [_P]),
     "cbn_domain_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "cbn_encode_f32": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P]),
+    "cbn_domain_f32_multi": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int64, _P, _P, _P]),
+    "cbn_encode_f32_multi": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
     "cbn_count_plan_create": (C.c_int, [_P, C.POINTER(Family), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "cbn_count_plan_destroy": (None, [_P]),
     "cbn_count_run": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),

@@ -109,9 +109,14 @@ __device__ __forceinline__ bool set_insert(uint32_t* set, uint32_t bits) {
   return false;
 }
 
-__global__ void domain_init_kernel(uint32_t* gset, int* overflow) {
+constexpr int DOM_MAX_COLS = 256;          // columns per multi-column launch (pointers travel as a kernel parameter)
+struct ColPtrs { const float* p[DOM_MAX_COLS]; };
+
+// one set (+ overflow flag) per column: column c at gset + c * (DOM_SLOTS + 1)
+__global__ void domain_init_kernel(uint32_t* gset_all) {
+  uint32_t* gset = gset_all + size_t(blockIdx.x) * (DOM_SLOTS + 1);
   for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) gset[i] = DOM_EMPTY;
-  if (threadIdx.x == 0) *overflow = 0;
+  if (threadIdx.x == 0) gset[DOM_SLOTS] = 0;
 }
 
 __device__ __forceinline__ bool domain_note(uint32_t* sset, uint32_t b, uint32_t& last, int* overflow) {
@@ -128,8 +133,10 @@ __device__ __forceinline__ bool domain_note(uint32_t* sset, uint32_t b, uint32_t
 
 // 128-bit loads, four values per thread and iteration (the column base is 16-byte aligned when VEC)
 template <bool VEC>
-__global__ void __launch_bounds__(256) domain_scan_kernel(const float* __restrict__ col, int64_t n,
-                                                          uint32_t* gset, int* overflow) {
+__global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant__ ColPtrs cols, int64_t n, uint32_t* gset_all) {
+  const float* __restrict__ col = cols.p[blockIdx.y];
+  uint32_t* gset = gset_all + size_t(blockIdx.y) * (DOM_SLOTS + 1);
+  int* overflow = reinterpret_cast<int*>(gset + DOM_SLOTS);
   __shared__ uint32_t sset[DOM_SLOTS];
   for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) sset[i] = DOM_EMPTY;
   __syncthreads();
@@ -163,8 +170,11 @@ __global__ void __launch_bounds__(256) domain_scan_kernel(const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(DOM_SLOTS) domain_finish_kernel(const uint32_t* gset, const int* overflow,
-                                                                  float* domain_out, int32_t* card_out) {
+__global__ void __launch_bounds__(DOM_SLOTS) domain_finish_kernel(const uint32_t* gset_all, float* domain_all, int32_t* card_all) {
+  const uint32_t* gset = gset_all + size_t(blockIdx.x) * (DOM_SLOTS + 1);
+  const int* overflow = reinterpret_cast<const int*>(gset + DOM_SLOTS);
+  float* domain_out = domain_all + size_t(blockIdx.x) * 256;
+  int32_t* card_out = card_all + blockIdx.x;
   __shared__ float vals[DOM_SLOTS];
   __shared__ int s_n;
   if (threadIdx.x == 0) s_n = 0;
@@ -197,34 +207,59 @@ __global__ void __launch_bounds__(DOM_SLOTS) domain_finish_kernel(const uint32_t
 }
 }  // namespace
 
+extern "C" int cbn_domain_f32_multi(cbn_ctx* ctx, const float* const* cols, int32_t n_cols, int64_t n, float* domains_out,
+                                    int32_t* cards_out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_domain_f32_multi: ctx is NULL");
+  if (!cols || n_cols < 1 || !domains_out || !cards_out || n < 0)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_domain_f32_multi: bad argument");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int c0 = 0; c0 < n_cols; c0 += DOM_MAX_COLS) {
+    const int nc = std::min(DOM_MAX_COLS, n_cols - c0);
+    ColPtrs cp{};
+    bool aligned = true;
+    for (int c = 0; c < nc; ++c) {
+      if (!cols[c0 + c]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_domain_f32_multi: column %d is NULL", c0 + c);
+      cp.p[c] = cols[c0 + c];
+      aligned = aligned && is_aligned(cols[c0 + c], 16);
+    }
+    uint32_t* gset = nullptr;
+    CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&gset, size_t(nc) * (DOM_SLOTS + 1) * sizeof(uint32_t), s));
+    domain_init_kernel<<<nc, 256, 0, s>>>(gset);
+    if (n > 0) {
+      // enough CTAs to fill the machine across all columns of the launch
+      int bx = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), std::max(1, (ctx->sm_count * 8 + nc - 1) / nc));
+      dim3 grid(std::max(bx, 1), nc);
+      if (aligned) domain_scan_kernel<true><<<grid, 256, 0, s>>>(cp, n, gset);
+      else domain_scan_kernel<false><<<grid, 256, 0, s>>>(cp, n, gset);
+    }
+    domain_finish_kernel<<<nc, DOM_SLOTS, 0, s>>>(gset, domains_out + size_t(c0) * 256, cards_out + c0);
+    CBN_CHECK_LAUNCH(ctx);
+    CBN_CUDA(ctx, cudaFreeAsync(gset, s));
+  }
+  return CBN_OK;
+}
+
 extern "C" int cbn_domain_f32(cbn_ctx* ctx, const float* col, int64_t n, float* domain_out, int32_t* card_out,
                               cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_domain_f32: ctx is NULL");
   if (!col || !domain_out || !card_out || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_domain_f32: bad argument");
-  DeviceGuard g(ctx->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  uint32_t* gset = nullptr;
-  CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&gset, (DOM_SLOTS + 1) * sizeof(uint32_t), s));
-  int* overflow = reinterpret_cast<int*>(gset + DOM_SLOTS);
-  domain_init_kernel<<<1, 256, 0, s>>>(gset, overflow);
-  if (n > 0) {
-    int blocks = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), int64_t(ctx->sm_count) * 8);
-    if (is_aligned(col, 16)) domain_scan_kernel<true><<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
-    else domain_scan_kernel<false><<<std::max(blocks, 1), 256, 0, s>>>(col, n, gset, overflow);
-  }
-  domain_finish_kernel<<<1, DOM_SLOTS, 0, s>>>(gset, overflow, domain_out, card_out);
-  CBN_CHECK_LAUNCH(ctx);
-  CBN_CUDA(ctx, cudaFreeAsync(gset, s));
-  return CBN_OK;
+  return cbn_domain_f32_multi(ctx, &col, 1, n, domain_out, card_out, stream);
 }
 
 // =========================================================================== encode
 namespace {
+// blockIdx.y = column; column c reads domain dom_all + c * dom_pitch (card from card_dev[c] when given) and writes
+// codes_all + c * ld
 template <bool VEC>
-__global__ void __launch_bounds__(256) encode_f32_kernel(const float* __restrict__ col, int64_t n,
-                                                         const float* __restrict__ dom, int card,
-                                                         uint8_t* __restrict__ codes,
-                                                         unsigned long long* n_unseen) {
+__global__ void __launch_bounds__(256) encode_f32_kernel(const __grid_constant__ ColPtrs cols, int64_t n,
+                                                         const float* __restrict__ dom_all, int dom_pitch, int card_arg,
+                                                         const int32_t* __restrict__ card_dev, uint8_t* __restrict__ codes_all,
+                                                         int64_t ld, unsigned long long* n_unseen) {
+  const float* __restrict__ col = cols.p[blockIdx.y];
+  const float* __restrict__ dom = dom_all + size_t(blockIdx.y) * dom_pitch;
+  uint8_t* __restrict__ codes = codes_all + int64_t(blockIdx.y) * ld;
+  const int card = card_dev ? max(0, min(card_dev[blockIdx.y], 255)) : card_arg;
   __shared__ float sdom[256];
   for (int i = threadIdx.x; i < card; i += blockDim.x) sdom[i] = dom[i];
   __syncthreads();
@@ -270,9 +305,39 @@ extern "C" int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const f
   bool vec = is_aligned(col, 16) && is_aligned(codes_out, 4);
   int64_t work = vec ? (n + 3) / 4 : n;
   int blocks = (int)std::min<int64_t>((work + 255) / 256, int64_t(ctx->sm_count) * 16);
-  if (vec) encode_f32_kernel<true><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
-  else encode_f32_kernel<false><<<blocks, 256, 0, s>>>(col, n, sorted_domain, card, codes_out, n_unseen);
+  ColPtrs cp{};
+  cp.p[0] = col;
+  if (vec) encode_f32_kernel<true><<<blocks, 256, 0, s>>>(cp, n, sorted_domain, 0, card, nullptr, codes_out, 0, n_unseen);
+  else encode_f32_kernel<false><<<blocks, 256, 0, s>>>(cp, n, sorted_domain, 0, card, nullptr, codes_out, 0, n_unseen);
   CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
+
+extern "C" int cbn_encode_f32_multi(cbn_ctx* ctx, const float* const* cols, int32_t n_cols, int64_t n, const float* domains,
+                                    const int32_t* cards_dev, uint8_t* codes_out, int64_t ld, unsigned long long* n_unseen,
+                                    cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_encode_f32_multi: ctx is NULL");
+  if (!cols || n_cols < 1 || !domains || !cards_dev || !codes_out || n < 0 || ld < n)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_encode_f32_multi: bad argument");
+  if (n == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int c0 = 0; c0 < n_cols; c0 += DOM_MAX_COLS) {
+    const int nc = std::min(DOM_MAX_COLS, n_cols - c0);
+    ColPtrs cp{};
+    bool vec = (ld % 4) == 0 && is_aligned(codes_out, 4);
+    for (int c = 0; c < nc; ++c) {
+      if (!cols[c0 + c]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_encode_f32_multi: column %d is NULL", c0 + c);
+      cp.p[c] = cols[c0 + c];
+      vec = vec && is_aligned(cols[c0 + c], 16);
+    }
+    const int64_t work = vec ? (n + 3) / 4 : n;
+    const int bx = (int)std::min<int64_t>((work + 255) / 256, std::max(1, (ctx->sm_count * 16 + nc - 1) / nc));
+    dim3 grid(std::max(bx, 1), nc);
+    if (vec) encode_f32_kernel<true><<<grid, 256, 0, s>>>(cp, n, domains + size_t(c0) * 256, 256, 0, cards_dev + c0, codes_out + int64_t(c0) * ld, ld, n_unseen);
+    else encode_f32_kernel<false><<<grid, 256, 0, s>>>(cp, n, domains + size_t(c0) * 256, 256, 0, cards_dev + c0, codes_out + int64_t(c0) * ld, ld, n_unseen);
+    CBN_CHECK_LAUNCH(ctx);
+  }
   return CBN_OK;
 }
 

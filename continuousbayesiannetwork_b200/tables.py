@@ -47,6 +47,9 @@ class DiscreteTables:
         self.joint: Optional[torch.Tensor] = None    # float32 [total_cells]
         self.cond: Optional[torch.Tensor] = None     # float32 [total_cells]
         self._count_plan = None
+        self._dom_matrix = None
+        self._layout_cards: Optional[List[int]] = None
+        self._counts_buf: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ layout
     def set_domains(self, domains: Sequence[torch.Tensor]):
@@ -54,6 +57,7 @@ class DiscreteTables:
         assert len(domains) == len(self.names)
         self.domains = [d.to(self.device, torch.float32).contiguous() for d in domains]
         self.cards = [int(d.numel()) for d in self.domains]
+        self._dom_matrix = None
         for n, c in zip(self.names, self.cards):
             if not 1 <= c <= N.MAX_CARD:
                 raise ValueError(f"variable {n} has {c} distinct values; the discrete path supports 1..{N.MAX_CARD}")
@@ -64,7 +68,15 @@ class DiscreteTables:
         self.set_domains([torch.arange(int(c), dtype=torch.float32) for c in cards])
 
     def _layout(self):
+        if self.fams is not None and self._layout_cards == self.cards and self._counts_buf is not None:
+            # same structure and cardinalities as before (a re-fit): keep the tables' layout and the count plan
+            self._counts_buf.zero_()
+            self.joint = None
+            self.cond = None
+            self._n_host, self._n_host_valid = 0, True
+            return
         self._destroy_plan()
+        self._layout_cards = list(self.cards)
         fams = (N.Family * len(self.names))()
         self.offsets, self.n_cells = [], []
         off = 0
@@ -146,17 +158,20 @@ class DiscreteTables:
         return dom[:c].clone()
 
     def discover_domains(self, cols: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        """``discover_domain`` for many columns with ONE host synchronisation (all scans are enqueued first)."""
+        """``discover_domain`` for many columns: one multi-column launch sequence (``cbn_domain_f32_multi``) and ONE
+        host synchronisation."""
         k = len(cols)
-        dom = torch.empty((k, 256), dtype=torch.float32, device=self.device)
-        card = torch.empty(k, dtype=torch.int32, device=self.device)
-        keep = []
-        for i, col in enumerate(cols):
-            col = col.to(self.device, torch.float32).contiguous()
-            keep.append(col)
-            N.check(N.lib().cbn_domain_f32(self.ctx.handle, col.data_ptr(), col.numel(), dom[i].data_ptr(), card[i:].data_ptr(),
-                                           N.stream_ptr(self.device)), self.ctx.handle)
-        cards = card.cpu().tolist()
+        n = int(cols[0].numel()) if k else 0
+        dom = torch.empty((max(k, 1), 256), dtype=torch.float32, device=self.device)
+        card = torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
+        keep = [c.to(self.device, torch.float32).contiguous() for c in cols]
+        for c in keep:
+            if c.numel() != n:
+                raise ValueError("all columns must have the same number of rows")
+        if k:
+            N.check(N.lib().cbn_domain_f32_multi(self.ctx.handle, N.ptr_array([c.data_ptr() for c in keep]), k, n, dom.data_ptr(),
+                                                 card.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
+        cards = card.cpu().tolist()[:k]
         for i, c in enumerate(cards):
             if c < 0:
                 raise ValueError(
@@ -174,12 +189,29 @@ class DiscreteTables:
         ld = _round_up(max(n, 1), 16)
         return torch.empty((len(self.names), ld), dtype=torch.uint8, device=self.device)
 
+    def _domain_matrix(self):
+        """All domains as one device matrix [n_vars, 256] + cardinalities (built once per ``set_domains``)."""
+        if self._dom_matrix is None:
+            host = torch.zeros((len(self.names), 256), dtype=torch.float32)
+            doms = torch.cat([d.reshape(-1) for d in self.domains]).cpu()          # one D2H copy
+            at = 0
+            for i, c in enumerate(self.cards):
+                host[i, :c] = doms[at: at + c]
+                at += c
+            self._dom_matrix = (host.to(self.device), torch.tensor(self.cards, dtype=torch.int32, device=self.device))
+        return self._dom_matrix
+
     def encode_columns(self, cols: Dict[str, torch.Tensor], strict: bool = True) -> torch.Tensor:
+        """float32 columns (by node name) -> uint8 code matrix [n_vars, ld], all columns in one launch."""
         n = int(next(iter(cols.values())).numel())
         codes = self.new_code_matrix(n)
         unseen = torch.zeros(1, dtype=torch.int64, device=self.device)
-        for name in self.names:
-            self.encode(cols[name].reshape(-1), self.index[name], codes[self.index[name]], unseen)
+        k = len(self.names)
+        keep = [cols[name].reshape(-1).to(self.device, torch.float32).contiguous() for name in self.names]
+        dom, card = self._domain_matrix()
+        N.check(N.lib().cbn_encode_f32_multi(self.ctx.handle, N.ptr_array([c.data_ptr() for c in keep]), k, n, dom.data_ptr(),
+                                             card.data_ptr(), codes.data_ptr(), codes.stride(0), unseen.data_ptr(),
+                                             N.stream_ptr(self.device)), self.ctx.handle)
         if strict and int(unseen.item()) != 0:
             raise ValueError(f"{int(unseen.item())} values are not in the fitted domains")
         return codes

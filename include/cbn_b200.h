@@ -95,6 +95,15 @@ CBN_API int cbn_domain_f32(cbn_ctx* ctx, const float* col, int64_t n, float* dom
                    cbn_stream stream);
 CBN_API int cbn_encode_f32(cbn_ctx* ctx, const float* col, int64_t n, const float* sorted_domain, int32_t card,
                    uint8_t* codes_out, unsigned long long* n_unseen, cbn_stream stream);
+/* the same for many columns at once (BayesianNetwork._train's loop over nodes, bayesian_network.py:138-160):
+ * cols: HOST array of n_cols device column pointers; domains_out: device float [n_cols][256]; cards_out: device
+ * int32 [n_cols]; codes_out: device uint8 [n_cols][ld].  cbn_encode_f32_multi reads the cardinalities from device
+ * memory (the output of cbn_domain_f32_multi), so the two calls need no host synchronisation between them. */
+CBN_API int cbn_domain_f32_multi(cbn_ctx* ctx, const float* const* cols, int32_t n_cols, int64_t n, float* domains_out,
+                         int32_t* cards_out, cbn_stream stream);
+CBN_API int cbn_encode_f32_multi(cbn_ctx* ctx, const float* const* cols, int32_t n_cols, int64_t n, const float* domains,
+                         const int32_t* cards_dev, uint8_t* codes_out, int64_t ld, unsigned long long* n_unseen,
+                         cbn_stream stream);
 
 /* ---- CPT counting -----------------------------------------------------------------
  * Replaces the sort-based torch.unique(dim=0, return_counts=True) of
