@@ -173,6 +173,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _bind_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch the pinned staging memory) on the CPU cores next to that GPU, so the
+    host<->device copies of the e2e path do not cross the socket interconnect."""
+    before = None
+    try:
+        import pynvml
+
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and w * 64 + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+    return before
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import numpy as np
@@ -187,6 +208,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = _bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peak_gbs, peak_src = _peaks()
@@ -411,6 +433,8 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core
             v, sample, cores = cpu_ve_queries_per_sec(args.cpu_budget_s)
             cpu = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
         line = {
