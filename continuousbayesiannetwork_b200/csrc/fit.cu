@@ -119,11 +119,17 @@ __global__ void domain_init_kernel(uint32_t* gset_all) {
   if (threadIdx.x == 0) gset[DOM_SLOTS] = 0;
 }
 
-__device__ __forceinline__ bool domain_note(uint32_t* sset, uint32_t b, uint32_t& last, int* overflow) {
-  if (b == last) return true;   // runs of equal values are the common case
-  last = b;
+// The last four distinct raw bit patterns a thread has seen sit in registers: for low-cardinality columns nearly every
+// value is recognised with four compares, without canonicalising, hashing or touching shared memory.
+struct Recent { uint32_t v0, v1, v2, v3; };
+
+__device__ __forceinline__ bool domain_note(uint32_t* sset, float x, Recent& r, int* overflow) {
+  const uint32_t raw = __float_as_uint(x);
+  if ((raw == r.v0) | (raw == r.v1) | (raw == r.v2) | (raw == r.v3)) return true;
+  r.v3 = r.v2; r.v2 = r.v1; r.v1 = r.v0; r.v0 = raw;
+  const uint32_t b = canon_bits(x);
   const uint32_t h = hash32(b) & (DOM_SLOTS - 1);
-  if (sset[h] == b) return true;   // fast path: already present at its home slot
+  if (sset[h] == b) return true;   // already present at its home slot
   if (!set_insert(sset, b)) {
     atomicExch(overflow, 1);       // more than DOM_SLOTS distinct values: not a discrete column
     return false;
@@ -131,7 +137,7 @@ __device__ __forceinline__ bool domain_note(uint32_t* sset, uint32_t b, uint32_t
   return true;
 }
 
-// 128-bit loads, four values per thread and iteration (the column base is 16-byte aligned when VEC)
+// 128-bit loads, eight values per thread and iteration (the column base is 16-byte aligned when VEC)
 template <bool VEC>
 __global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant__ ColPtrs cols, int64_t n, uint32_t* gset_all) {
   const float* __restrict__ col = cols.p[blockIdx.y];
@@ -141,8 +147,11 @@ __global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant_
   for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) sset[i] = DOM_EMPTY;
   __syncthreads();
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  uint32_t last = DOM_EMPTY;
+  // every thread's register cache starts with the column's first value; thread 0 enters that value into the set
+  const float first = __ldg(col);
+  Recent r{__float_as_uint(first), __float_as_uint(first), __float_as_uint(first), __float_as_uint(first)};
   bool ok = true;
+  if (threadIdx.x == 0) ok = set_insert(sset, canon_bits(first));
   if (VEC) {
     const int64_t n4 = n >> 2;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4 && ok; i += 2 * stride) {
@@ -150,16 +159,15 @@ __global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant_
       const bool two = i + stride < n4;
       float4 c = a;
       if (two) c = ld_nc_f128(reinterpret_cast<const float4*>(col) + i + stride);
-      ok = domain_note(sset, canon_bits(a.x), last, overflow) && domain_note(sset, canon_bits(a.y), last, overflow) &&
-           domain_note(sset, canon_bits(a.z), last, overflow) && domain_note(sset, canon_bits(a.w), last, overflow) &&
-           domain_note(sset, canon_bits(c.x), last, overflow) && domain_note(sset, canon_bits(c.y), last, overflow) &&
-           domain_note(sset, canon_bits(c.z), last, overflow) && domain_note(sset, canon_bits(c.w), last, overflow);
+      ok = domain_note(sset, a.x, r, overflow) && domain_note(sset, a.y, r, overflow) && domain_note(sset, a.z, r, overflow) &&
+           domain_note(sset, a.w, r, overflow) && domain_note(sset, c.x, r, overflow) && domain_note(sset, c.y, r, overflow) &&
+           domain_note(sset, c.z, r, overflow) && domain_note(sset, c.w, r, overflow);
     }
     for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n && ok; i += stride)
-      ok = domain_note(sset, canon_bits(__ldg(col + i)), last, overflow);
+      ok = domain_note(sset, __ldg(col + i), r, overflow);
   } else {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n && ok; i += stride)
-      ok = domain_note(sset, canon_bits(__ldg(col + i)), last, overflow);
+      ok = domain_note(sset, __ldg(col + i), r, overflow);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < DOM_SLOTS; i += blockDim.x) {
@@ -265,24 +273,46 @@ __global__ void __launch_bounds__(256) encode_f32_kernel(const __grid_constant__
   __syncthreads();
   unsigned int unseen = 0;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  // register cache of the last four distinct values and their codes: low-cardinality columns skip the binary search
+  const float first = __ldg(col);
+  const int first_code = domain_code(sdom, card, first);
+  uint32_t k0 = __float_as_uint(first), k1 = k0, k2 = k0, k3 = k0;
+  int e0 = first_code, e1 = first_code, e2 = first_code, e3 = first_code;
+  auto code_of = [&](float x) -> int {
+    const uint32_t raw = __float_as_uint(x);
+    if (raw == k0) return e0;
+    if (raw == k1) return e1;
+    if (raw == k2) return e2;
+    if (raw == k3) return e3;
+    const int c = domain_code(sdom, card, x);
+    k3 = k2; e3 = e2; k2 = k1; e2 = e1; k1 = k0; e1 = e0; k0 = raw; e0 = c;
+    return c;
+  };
   if (VEC) {
     const int64_t n4 = n >> 2;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      float4 v = ld_nc_f128(reinterpret_cast<const float4*>(col) + i);
-      int c0 = domain_code(sdom, card, v.x), c1 = domain_code(sdom, card, v.y);
-      int c2 = domain_code(sdom, card, v.z), c3 = domain_code(sdom, card, v.w);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+      const float4 v = ld_nc_f128(reinterpret_cast<const float4*>(col) + i);
+      const bool two = i + stride < n4;
+      float4 w = v;
+      if (two) w = ld_nc_f128(reinterpret_cast<const float4*>(col) + i + stride);
+      const int c0 = code_of(v.x), c1 = code_of(v.y), c2 = code_of(v.z), c3 = code_of(v.w);
       unseen += (c0 == CBN_UNSEEN) + (c1 == CBN_UNSEEN) + (c2 == CBN_UNSEEN) + (c3 == CBN_UNSEEN);
       reinterpret_cast<uint32_t*>(codes)[i] = uint32_t(c0) | (uint32_t(c1) << 8) | (uint32_t(c2) << 16) | (uint32_t(c3) << 24);
+      if (two) {
+        const int d0 = code_of(w.x), d1 = code_of(w.y), d2 = code_of(w.z), d3 = code_of(w.w);
+        unseen += (d0 == CBN_UNSEEN) + (d1 == CBN_UNSEEN) + (d2 == CBN_UNSEEN) + (d3 == CBN_UNSEEN);
+        reinterpret_cast<uint32_t*>(codes)[i + stride] = uint32_t(d0) | (uint32_t(d1) << 8) | (uint32_t(d2) << 16) | (uint32_t(d3) << 24);
+      }
     }
     // tail
     for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-      int c = domain_code(sdom, card, col[i]);
+      int c = code_of(col[i]);
       unseen += (c == CBN_UNSEEN);
       codes[i] = (uint8_t)c;
     }
   } else {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-      int c = domain_code(sdom, card, col[i]);
+      int c = code_of(col[i]);
       unseen += (c == CBN_UNSEEN);
       codes[i] = (uint8_t)c;
     }
