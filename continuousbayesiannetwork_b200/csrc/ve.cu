@@ -205,9 +205,18 @@ __device__ __forceinline__ void load_slice_l2(const float* __restrict__ src, flo
   }
 }
 
+// Programmatic dependent launch: a gather kernel lets the next kernel of its stream start while it is still running
+// (pdl_trigger at entry) and only orders its own STORES behind the previous kernel (pdl_wait before the first store), so
+// back-to-back launches on one stream overlap their launch latency, prologue and evidence loads.  Both are no-ops for
+// launches without the programmatic-serialization attribute; a kernel that is not one of these never triggers early, so
+// ordinary stream order holds towards everybody else's kernels.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int CT>
 __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad,
                                              int64_t n_rows, float* __restrict__ out, uint64_t st_pol = 0) {
+  pdl_wait();
   if (normalize) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -445,6 +454,7 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned
                                                                   int desc_bytes, const uint8_t* __restrict__ ev, int64_t ld,
                                                                   int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
   const GTable& T = *reinterpret_cast<const GTable*>(smem_raw);
   const float* base = T.smem_off >= 0 ? reinterpret_cast<const float*>(smem_raw + desc_bytes) + T.smem_off : T.data;
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned
                                                                   int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
+  pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
   GTable* st = reinterpret_cast<GTable*>(smem_raw);
   // descriptors address evidence slots; inside this kernel they address staged tile columns
@@ -562,6 +573,7 @@ __global__ void __launch_bounds__(GATHER_TPB, gather_min_blocks(CT)) gather_code
     const unsigned char* __restrict__ blob, int blob_bytes, int desc_bytes, int n_tables, const uint8_t* __restrict__ ev,
     int64_t ld, int64_t n_rows, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
   const GTable* st = reinterpret_cast<const GTable*>(smem_raw);
   const float* pool = reinterpret_cast<const float*>(smem_raw + desc_bytes);
@@ -793,6 +805,24 @@ extern "C" void cbn_ve_plan_destroy(cbn_ve_plan* p) {
 }
 
 namespace {
+// launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); CBN_PDL=0 turns it off
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("CBN_PDL"); pdl = e ? atoi(e) : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 int gather_blocks(cbn_ctx* ctx, int64_t n_rows, int per_sm) {
   const int64_t nquads = (n_rows + 3) >> 2;
   return (int)std::max<int64_t>(1, std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * per_sm));
@@ -813,9 +843,8 @@ int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     occ_smem = p->blob_bytes;
   }
   const int per_sm = std::max(occ, 1);
-  gather_codes_kernel<CT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
-      p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, outs);
-  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, launch_pdl(gather_codes_kernel<CT>, gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s,
+                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, outs));
   return CBN_OK;
 }
 template <int CT>
@@ -849,9 +878,8 @@ int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     occ_smem = p->blob_bytes;
   }
   const int per_sm = std::max(occ, 1);
-  gather_inter_kernel<CT, NOUT><<<gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s>>>(
-      p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, outs);
-  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, launch_pdl(gather_inter_kernel<CT, NOUT>, gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s,
+                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, outs));
   return CBN_OK;
 }
 
@@ -889,9 +917,8 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
   const int per_sm = std::max(occ, 1);
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, int64_t(ctx->sm_count) * per_sm));
-  gather_tiles_kernel<CT, NOUT><<<blocks, GATHER_TPB, smem, s>>>(p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, cols,
-                                                                 n_stages, hints, ev, ld, n_rows, outs);
-  CBN_CHECK_LAUNCH(ctx);
+  CBN_CUDA(ctx, launch_pdl(gather_tiles_kernel<CT, NOUT>, blocks, GATHER_TPB, smem, s, p->d_blob, (int)p->blob_bytes,
+                           (int)p->desc_bytes, p->n_tables, cols, n_stages, hints, ev, ld, n_rows, outs));
   return CBN_OK;
 }
 
