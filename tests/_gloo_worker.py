@@ -21,8 +21,11 @@ def main():
     codes = synth.sample_forward_numpy(spec, 3, s, e - s)
     fams = [spec.parents[i] + [i] for i in range(spec.n)]
     local = np.concatenate([O.dense_counts(codes, f, spec.cards).reshape(-1) for f in fams])
-    t = torch.from_numpy(local.copy())
+    # tables and the local sample count travel in ONE buffer (DiscreteTables.allreduce_buffer): a single collective
+    t = torch.from_numpy(np.concatenate([local, [e - s, 0]]).astype(np.int64))
     sharding.allreduce_counts(t)
+    assert int(t[-2]) == n and int(t[-1]) == 0
+    t = t[:-2]
     full_codes = synth.sample_forward_numpy(spec, 3, 0, n)
     want = np.concatenate([O.dense_counts(full_codes, f, spec.cards).reshape(-1) for f in fams])
     assert np.array_equal(t.numpy(), want)
