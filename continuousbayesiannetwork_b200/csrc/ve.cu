@@ -1422,11 +1422,14 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     if (!posteriors_host[o]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: posterior %d is NULL", o);
   if (n_rows == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
-  // rows per chunk: half the call (so the H2D copy and the kernel of the second half hide behind the D2H copy of the
-  // first), between 256K and 1M rows -- PCIe copies below ~4 MB lose bandwidth to per-copy overhead (52 vs 57 GB/s
-  // measured), chunks above 1M rows only add start-up latency.  Mapped (zero-copy) access from the kernel was measured
-  // slower than the copy engines in both directions (45 GB/s stores; tools/exp_e2e.py) and is not used.
-  const int64_t chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 18, ((n_rows / 2 + 65535) >> 16) << 16));
+  // Chunking.  The D2H copies of the posteriors are the long pole (8 bytes per binary query against 1 byte per evidence
+  // value), so the schedule keeps the D2H engine busy from as early as possible to the end: a short LEAD chunk (128K rows)
+  // gets the first posteriors on their way after ~15 us, the rest goes in chunks of half the remainder (256K..1M rows):
+  // PCIe copies below ~4 MB lose bandwidth to per-copy overhead (52 vs 57 GB/s measured), chunks above 1M rows add nothing.
+  // Mapped (zero-copy) access from the kernel was measured slower than the copy engines in both directions (45 GB/s
+  // stores; tools/exp_e2e.py) and is not used.
+  const int64_t lead = n_rows > (1 << 18) ? (1 << 17) : n_rows;
+  const int64_t chunk = std::max<int64_t>(lead, std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 18, (((n_rows - lead) / 2 + 65535) >> 16) << 16)));
   const int ne = std::max(plan->n_evidence, 1);
   const size_t out_stride = size_t(chunk) * ct;   // floats per output inside a staging buffer
   int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float));
@@ -1444,8 +1447,8 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
       memcpy(posteriors_host[o] + pending_row[b] * ct, (float*)ctx->io_pin_out[b] + o * out_stride, size_t(pending_m[b]) * ct * sizeof(float));
   };
   int b = 0;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, b ^= 1) {
-    const int64_t m = std::min(chunk, n_rows - r0);
+  for (int64_t r0 = 0, m = 0; r0 < n_rows; r0 += m, b ^= 1) {
+    m = r0 == 0 ? lead : std::min(chunk, n_rows - r0);
     cudaStream_t s = ctx->io_stream[b];
     // buffer b is free once its previous D2H has been consumed
     if (pending_row[b] >= 0) {
