@@ -113,3 +113,42 @@ def test_count_allreduce_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=110, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def test_incremental_greedy_matches_full_rescan():
+    """The planner's incremental bookkeeping (cached elimination scopes, updated only around the eliminated variable)
+    must pick exactly what a full rescan of every hidden variable picks at every step."""
+    from continuousbayesiannetwork_b200.ve import _Greedy
+
+    rng = np.random.default_rng(7)
+    for trial in range(30):
+        n = int(rng.integers(8, 40))
+        cards = [int(c) for c in rng.integers(2, 6, size=n)]
+        scopes = {}
+        for k in range(n):                                  # family-like factors: a node and up to 3 earlier nodes
+            ps = rng.choice(k, size=min(k, int(rng.integers(0, 4))), replace=False) if k else []
+            scopes[k] = [int(p) for p in ps] + [k]
+        hidden = [int(v) for v in rng.choice(n, size=int(rng.integers(1, n)), replace=False)]
+        g = _Greedy(cards, scopes, hidden)
+        ref = {k: list(v) for k, v in scopes.items()}
+        left = set(hidden)
+        nk = n
+        while left:
+            best = None
+            for v in sorted(left):
+                sc = set()
+                for s in ref.values():
+                    if v in s:
+                        sc |= set(s)
+                sc.discard(v)
+                c = int(np.prod([cards[u] for u in sc])) if sc else 1
+                if best is None or (c, v) < (best[0], best[1]):
+                    best = (c, v, sc)
+            v, c, sc = g.best()
+            assert (c, v, set(sc)) == (best[0], best[1], best[2]), trial
+            ref = {k: s for k, s in ref.items() if v not in s}
+            ref[nk] = sorted(sc)
+            g.eliminate(v, nk, sorted(sc))
+            left.discard(v)
+            nk += 1
+        assert not g.hidden
