@@ -12,19 +12,39 @@
 
 // =========================================================================== contraction
 namespace {
-__global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ cbn_contract d, long long n_out) {
+// Division by an axis cardinality as multiply + shift: with L = ceil(log2 card), sh = 32 + L and m = ceil(2^sh / card)
+// (< 2^33), (rem * m) >> sh == rem / card exactly for every rem < 2^31: the product stays below 2^64 and the error term
+// rem / 2^sh < 2^-(L+1) <= 1 / (2 card) cannot reach the next integer.  Decoding an output index then costs a multiply
+// and a shift per axis instead of a 64-bit division.
+struct ContractMagic { unsigned long long m[CBN_MAX_CONTRACT_DIMS]; int sh[CBN_MAX_CONTRACT_DIMS]; };
+
+template <bool FAST>
+__global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ cbn_contract d, const __grid_constant__ ContractMagic mg,
+                                                       long long n_out) {
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
        o += (long long)gridDim.x * blockDim.x) {
-    long long rem = o;
     long long base[CBN_MAX_CONTRACT_INPUTS];
 #pragma unroll
     for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k) base[k] = 0;
-    for (int a = d.n_out_dims - 1; a >= 0; --a) {
-      const int c = (int)(rem % d.out_card[a]);
-      rem /= d.out_card[a];
+    if (FAST) {
+      unsigned rem = (unsigned)o;
+      for (int a = d.n_out_dims - 1; a >= 0; --a) {
+        const unsigned q = (unsigned)(((unsigned long long)rem * mg.m[a]) >> mg.sh[a]);
+        const int c = (int)(rem - q * (unsigned)d.out_card[a]);
+        rem = q;
 #pragma unroll
-      for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
-        if (k < d.n_in) base[k] += (long long)c * d.in_stride[k][a];
+        for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+          if (k < d.n_in) base[k] += (long long)c * d.in_stride[k][a];
+      }
+    } else {
+      long long rem = o;
+      for (int a = d.n_out_dims - 1; a >= 0; --a) {
+        const int c = (int)(rem % d.out_card[a]);
+        rem /= d.out_card[a];
+#pragma unroll
+        for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+          if (k < d.n_in) base[k] += (long long)c * d.in_stride[k][a];
+      }
     }
     float acc = 0.0f;
     for (int s = 0; s < d.sum_card; ++s) {
@@ -66,7 +86,18 @@ extern "C" int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_s
   DeviceGuard g(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   int blocks = (int)std::min<long long>((n_out + 255) / 256, (long long)ctx->sm_count * 16);
-  contract_kernel<<<blocks, 256, 0, s>>>(*desc, n_out);
+  bool fast = n_out < (1ll << 31);
+  ContractMagic mg{};
+  for (int a = 0; a < desc->n_out_dims; ++a) {
+    const unsigned long long card = (unsigned long long)desc->out_card[a];
+    fast = fast && card <= 65536;
+    int L = 0;
+    while ((1ull << L) < card) ++L;
+    mg.sh[a] = 32 + L;
+    mg.m[a] = ((1ull << mg.sh[a]) + card - 1) / card;
+  }
+  if (fast) contract_kernel<true><<<blocks, 256, 0, s>>>(*desc, mg, n_out);
+  else contract_kernel<false><<<blocks, 256, 0, s>>>(*desc, mg, n_out);
   CBN_CHECK_LAUNCH(ctx);
   if (desc->normalize_last && desc->n_out_dims > 0) {
     int card = desc->out_card[desc->n_out_dims - 1];

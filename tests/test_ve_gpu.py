@@ -133,6 +133,34 @@ def test_config5_layered_dag_shallow_patterns():
     assert done >= 12 and kinds == {True, False}
 
 
+def test_contraction_kernel_on_large_outputs():
+    """``cbn_factor_contract`` against torch.einsum on outputs of 2^28+ cells with 10 axes of mixed cardinalities: the
+    index decoding (multiply + shift per axis) must stay exact where the running remainder is close to 2^31."""
+    from continuousbayesiannetwork_b200.tables import DiscreteTables
+    from continuousbayesiannetwork_b200.ve import Factor, VECompiler
+
+    cards = [7, 3, 8, 5, 2, 6, 4, 255, 9, 3, 2]                     # variables 0..10; variable 10 is summed out
+    names = [f"v{i}" for i in range(len(cards))]
+    t = DiscreteTables(names, {}, device=DEV)
+    t.set_cards(cards)
+    c = VECompiler(t)
+    g = torch.Generator(device=DEV); g.manual_seed(4)
+    a_scope, b_scope = [0, 2, 4, 7, 10], [1, 3, 5, 6, 8, 9, 10]
+    A = torch.rand([cards[v] for v in a_scope], device=DEV, generator=g)
+    B = torch.rand([cards[v] for v in b_scope], device=DEV, generator=g)
+    out_scope = [7, 0, 1, 2, 3, 4, 5, 6, 8, 9]                      # 277,603,200 cells (1.1 GB of float32)
+    n_out = int(np.prod([cards[v] for v in out_scope]))
+    assert 1 << 28 < n_out < 1 << 31
+    got = c._contract([Factor(a_scope, A.reshape(-1)), Factor(b_scope, B.reshape(-1))], out_scope, 10, dry=False).tensor
+    letters = "abcdefghijk"
+    expr = "".join(letters[v] for v in a_scope) + "," + "".join(letters[v] for v in b_scope) + "->" + "".join(letters[v] for v in out_scope)
+    want = torch.einsum(expr, A, B).reshape(-1)
+    assert got.numel() == n_out
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=0)
+    del got, want
+    torch.cuda.empty_cache()
+
+
 def test_empty_and_tiny_batches():
     from continuousbayesiannetwork_b200 import synth
     from continuousbayesiannetwork_b200.engine import install_cpts
