@@ -546,6 +546,25 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
                              "frac_of_hbm_peak": n_in * spec.n * 10 * 5 / sec / 1e9 / peak_gbs}
     del cols, ing
     torch.cuda.empty_cache()
+    # fit end to end from HOST codes (pinned): chunked H2D overlapped with counting, then CPTs (Asia, 2^26 samples)
+    spec = synth.asia()
+    n_h = 1 << 26
+    th = tables_from_spec(spec, dev)
+    hcodes = sample_network(spec, seed=98, first=rank * n_h, n=n_h, device=dev, tables=th).cpu().pin_memory()
+    th.count_host(hcodes, n_h)
+    torch.cuda.synchronize()
+    barrier_t0 = time.perf_counter()
+    for _ in range(3):
+        th.counts.zero_()
+        th.n_total = 0
+        th.count_host(hcodes, n_h)
+        th.finalize()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - barrier_t0
+    out["fit_e2e"] = {"metric": "CPT-fit samples/sec, pinned host codes in (H2D inside the timed region)", "value": n_h * 3 / el * world,
+                      "unit": "samples/s", "samples_per_gpu": n_h, "n_vars": spec.n, "h2d_bytes_per_step": n_h * spec.n,
+                      "pcie_GBs": n_h * spec.n * 3 / el / 1e9, "call": "cbn_count_run_host + cbn_cpt_from_plan_dev"}
+    del hcodes, th
     # config 3: Alarm-shaped, 16M evidence rows sharded over the ranks (strong scaling inside this extra)
     spec = synth.alarm()
     tables, infer = install_cpts(spec, dev)

@@ -101,6 +101,7 @@ SIGNATURES = {
     "cbn_count_plan_create": (C.c_int, [_P, C.POINTER(Family), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "cbn_count_plan_destroy": (None, [_P]),
     "cbn_count_run": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "cbn_count_run_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
     "cbn_count_plan_groups": (C.c_int, [_P]),
     "cbn_count_plan_updates_per_sample": (C.c_int, [_P]),
     "cbn_cpt_from_counts": (C.c_int, [_P, _P, C.POINTER(Family), C.c_int32, C.c_longlong, _P, _P, _P]),

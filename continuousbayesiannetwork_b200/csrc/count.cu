@@ -18,6 +18,7 @@
 // count_direct_kernel is the same arithmetic straight from global memory: used for the tail
 // (n % 2048 samples) and, with global atomics, for families too large for shared memory.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <new>
@@ -792,6 +793,58 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
       CBN_CHECK_LAUNCH(ctx);
     }
   }
+  return CBN_OK;
+}
+
+// host code matrix in, device count tables out: chunks of samples go H2D (one strided copy for all columns of a chunk)
+// on two alternating streams while the previous chunk is being counted; the tables accumulate as in cbn_count_run
+extern "C" int cbn_count_run_host(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes_host, int64_t ld, int64_t n,
+                                  unsigned long long* counts) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run_host: ctx is NULL");
+  if (!plan || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run_host: bad argument");
+  if (n == 0) return CBN_OK;
+  if (!codes_host || !counts || ld < n) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run_host: bad argument");
+  DeviceGuard g(ctx->device);
+  const int n_cols = plan->n_cols;
+  // ~32 MB per chunk (at least 64K samples, a multiple of the largest tile so only the last chunk has a tail)
+  int64_t chunk = std::max<int64_t>(1 << 16, (int64_t(32) << 20) / std::max(n_cols, 1));
+  chunk = std::min<int64_t>((chunk + 8191) & ~int64_t(8191), (n + 8191) & ~int64_t(8191));
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->io_stream[i]) CBN_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_stream[i], cudaStreamNonBlocking));
+  }
+  const size_t need = size_t(chunk) * n_cols;
+  if (need > ctx->io_in_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->io_dev_in[i]) cudaFree(ctx->io_dev_in[i]);
+      if (ctx->io_pin_in[i]) cudaFreeHost(ctx->io_pin_in[i]);
+      ctx->io_dev_in[i] = nullptr; ctx->io_pin_in[i] = nullptr;
+      CBN_CUDA(ctx, cudaMalloc(&ctx->io_dev_in[i], need));
+      CBN_CUDA(ctx, cudaMallocHost(&ctx->io_pin_in[i], need));
+    }
+    ctx->io_in_bytes = need;
+  }
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, codes_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  // the counts may still be in use by work queued on the caller's stream: this entry point is synchronous, so order
+  // behind everything on the device first
+  CBN_CUDA(ctx, cudaDeviceSynchronize());
+  int b = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += chunk, b ^= 1) {
+    const int64_t m = std::min(chunk, n - s0);
+    cudaStream_t s = ctx->io_stream[b];
+    CBN_CUDA(ctx, cudaStreamSynchronize(s));       // the staging buffer's previous chunk has been counted
+    uint8_t* din = (uint8_t*)ctx->io_dev_in[b];
+    if (pinned) {
+      CBN_CUDA(ctx, cudaMemcpy2DAsync(din, size_t(chunk), codes_host + s0, size_t(ld), size_t(m), size_t(n_cols), cudaMemcpyHostToDevice, s));
+    } else {
+      for (int c = 0; c < n_cols; ++c) memcpy((uint8_t*)ctx->io_pin_in[b] + int64_t(c) * chunk, codes_host + int64_t(c) * ld + s0, m);
+      CBN_CUDA(ctx, cudaMemcpyAsync(din, ctx->io_pin_in[b], need, cudaMemcpyHostToDevice, s));
+    }
+    int rc = cbn_count_run(ctx, plan, din, chunk, m, counts, (cbn_stream)s);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 2; ++i) CBN_CUDA(ctx, cudaStreamSynchronize(ctx->io_stream[i]));
   return CBN_OK;
 }
 

@@ -229,6 +229,17 @@ class DiscreteTables:
         if self._n_host_valid:
             self._n_host += int(n)
 
+    def count_host(self, codes_host: torch.Tensor, n: int):
+        """``count`` for a HOST code matrix (uint8 [n_vars, ld], pinned or pageable): chunked copies overlap the counting."""
+        assert codes_host.dtype == torch.uint8 and codes_host.dim() == 2 and codes_host.shape[0] == len(self.names)
+        assert not codes_host.is_cuda and codes_host.stride(1) == 1
+        self._ensure_plan()
+        N.check(N.lib().cbn_count_run_host(self.ctx.handle, self._count_plan, codes_host.data_ptr(), codes_host.stride(0), int(n),
+                                           self.counts.data_ptr()), self.ctx.handle)
+        self._n_dev.add_(int(n))
+        if self._n_host_valid:
+            self._n_host += int(n)
+
     def _ensure_plan(self):
         if self._count_plan is None:
             h = C.c_void_p()

@@ -118,6 +118,10 @@ CBN_API int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t 
 CBN_API void cbn_count_plan_destroy(cbn_count_plan* plan);
 CBN_API int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
                   unsigned long long* counts, cbn_stream stream);
+/* the same from a HOST code matrix (pinned or pageable): chunked H2D copies overlap the counting; synchronous.
+ * counts: device int64 tables as above (they accumulate). */
+CBN_API int cbn_count_run_host(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes_host, int64_t ld, int64_t n,
+                       unsigned long long* counts);
 /* introspection for the bench: number of family groups (kernel passes over the tile) */
 CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
 /* table updates per sample after merging families that share variables into super-families (<= number of families) */

@@ -251,3 +251,27 @@ def test_sample_count_lives_on_the_device_next_to_the_tables():
     t.n_total = 0
     with pytest.raises(ValueError):
         t.finalize()
+
+
+def test_host_code_matrix_counts_like_the_device_path():
+    """``cbn_count_run_host``: pinned and pageable host matrices, several chunks, ragged tail, accumulation."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+
+    spec = synth.alarm()
+    n = 2_100_037                                   # 32 MB chunks of 37 columns: three chunks
+    codes = sample_network(spec, seed=17, first=0, n=n, device=DEV)
+    dev = tables_from_spec(spec, DEV)
+    dev.count(codes, n)
+    host = codes.cpu()
+    for buf in (host, host.pin_memory()):
+        t = tables_from_spec(spec, DEV)
+        t.count_host(buf, n)
+        assert torch.equal(t.counts, dev.counts) and t.n_total == n
+        t.count_host(buf[:, 1024:], 5000)           # a second call accumulates (offset keeps the 16-byte alignment)
+        extra = tables_from_spec(spec, DEV)
+        extra.count(codes[:, 1024:], 5000)
+        assert torch.equal(t.counts, dev.counts + extra.counts) and t.n_total == n + 5000
+    t = tables_from_spec(spec, DEV)
+    t.count_host(host, 0)
+    assert int(t.counts.sum()) == 0
