@@ -702,6 +702,15 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
         for plan, ev, o in pats:
             plan.run_codes(ev, rows, out=o)
 
+    # arithmetic of the per-row schedules: multiply-adds per row, timed separately from the gather plans
+    row_pats = [x for x in pats if isinstance(x[0], RowPlan)]
+    row_madds = sum(p.stats.per_row_madds for p, _, _ in row_pats)
+
+    def rstep(_i):
+        for plan, ev, o in row_pats:
+            plan.run_codes(ev, rows, out=o)
+
+    row_sec = timed(graphed(rstep), 3, 1) / 3 if row_pats else 0.0
     k = 3
     sec = timed(graphed(lstep), k, 1)
     alg = sum(rows * p.algorithmic_bytes_per_row() for p, _, _ in pats) * world
@@ -710,6 +719,10 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
                                                          "note": "induced width of the hidden part is 2^43+ cells for 63 of 64 patterns (DESIGN.md section 5)"},
                              "first_five_layers_patterns": {"attempted": 64, "compiled": len(pats), "per_row_plans": n_rowplans,
                                                             "plan_compile_ms_total": compile_ms},
+                             "per_row_plans": {"plans": len(row_pats), "multiply_adds_per_row_all_plans": row_madds,
+                                               "ms_per_pass": row_sec * 1e3,
+                                               "achieved_Gmadd_s": (row_madds * rows / row_sec / 1e9) if row_sec else None,
+                                               "note": "fp32 FMA peak of the part is ~37,000 Gmadd/s: the executor is bound by shared-memory / L1 latency per term, not by the FMA pipe"},
                              "rows_per_gpu_per_pattern": rows, "achieved_GBs": alg * k / sec / 1e9,
                              "frac_of_hbm_peak": alg * k / sec / 1e9 / (peak_gbs * world)}
     return out

@@ -51,6 +51,7 @@ class PlanStats:
     final_tables: List[Tuple[Tuple[int, ...], int]] = field(default_factory=list)
     support_unchecked: bool = False
     per_row_hidden: int = 0                      # hidden variables left to the per-row executor (0 = gather plan)
+    per_row_madds: int = 0                       # multiply-adds of the per-row schedule, per evidence row
     relevant_evidence: List[int] = field(default_factory=list)
 
 
@@ -623,6 +624,7 @@ class VECompiler:
             off_at += offs.size
             temp_total += (out_size + 3) // 4 * 4
             stats.contraction_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
+            stats.per_row_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
             return (n_in + len(steps) - 1, list(out_scope), strides_of(out_scope))
 
         def size_of(scope):
