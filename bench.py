@@ -481,6 +481,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": len(ASIA_EVIDENCE) * rows * world,
                     "d2h_bytes_per_step": len(ASIA_TARGETS) * rows * 2 * 4 * world,
                     "call": "cbn_ve_run_codes_host_multi (pinned host uint8 codes in, 3 pinned host fp32 posteriors out)",
+                    "timing": "host clock around the synchronous calls (each returns after its last D2H copy has landed), barrier + synchronize on both sides, max over ranks",
                     "python_api": {"value": api_value, "unit": "queries/s",
                                    "call": "ExactInference.infer(target, {name: pinned float32 [nq,1]}) -> pinned host copy"},
                     "python_api_many": {"value": many_value, "unit": "queries/s",
