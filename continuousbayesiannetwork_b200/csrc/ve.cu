@@ -155,6 +155,8 @@ struct cbn_ve_plan {
   void* d_row_steps = nullptr;
   void* d_row_offsets = nullptr;
   int rows_off_ints = 0;
+  size_t rows_thread_smem = 0;
+  bool rows_per_thread = false;
   float* d_inter = nullptr;      // fused plans with identical indexing: targets interleaved [cfg][target][t]
   int interleaved = 0;           // number of targets stored in d_inter (0 = not interleaved)
   unsigned char* d_blob = nullptr;  // [GTable x n_tables][staged table pool]: one straight copy into shared memory
@@ -1254,6 +1256,145 @@ __global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __
 }
 }  // namespace
 
+// ---- small schedules: one THREAD per row -----------------------------------------------------------------------
+// When the temporaries of a schedule are tiny (<= ROWT_MAX_TEMPS floats per row) a warp per row leaves most lanes idle and
+// pays a shuffle/sync round per step.  Here every thread runs the whole schedule for its own row: control flow is uniform
+// across the CTA (same steps, cells and terms for every row), the evidence codes are read coalesced (consecutive threads =
+// consecutive rows), temporaries live in shared memory as [cell][thread] (conflict-free), the static table slices are
+// gathered through L1 (the tables of such plans are small), and a step's offsets are shared-memory broadcasts.
+namespace {
+constexpr int ROWT_TPB = 128;
+constexpr int ROWT_MAX_TEMPS = 64;
+constexpr int ROWT_MAX_TERMS = 320;
+
+template <bool LOG, int NIN>
+__device__ __forceinline__ float rowt_step(const RowStepDev& S, const int* __restrict__ offs, const float* const* gsrc, const int* tsrc,
+                                           float* __restrict__ tsm, int tid) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float* g[NIN];
+  int t[NIN], ss[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) { g[k] = gsrc[k]; t[k] = tsrc[k]; ss[k] = S.sum_stride[k]; }
+  const int out_size = S.out_size, sum_card = S.sum_card;
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = 0; o < out_size; ++o) {
+    int off[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) off[k] = offs[k * out_size + o];
+    float acc = LOG ? NEG_INF : 0.0f;
+    for (int sv = 0; sv < sum_card; ++sv) {
+      float prod = LOG ? 0.0f : 1.0f;
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) {
+        const int idx = off[k] + sv * ss[k];
+        const float x = t[k] < 0 ? __ldg(g[k] + idx) : tsm[(t[k] + idx) * ROWT_TPB + tid];
+        prod = LOG ? prod + x : prod * x;
+      }
+      acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
+    }
+    tsm[(S.temp_off + o) * ROWT_TPB + tid] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  return mx;
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(ROWT_TPB) ve_rows_thread_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
+                                                                  const RowStepDev* __restrict__ steps, int n_steps, int temp_floats,
+                                                                  const int* __restrict__ off_pool, int off_ints,
+                                                                  const uint8_t* __restrict__ ev, int64_t ld, int64_t n_rows,
+                                                                  int card_t, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowStepDev* sst = reinterpret_cast<RowStepDev*>(smem_raw);
+  RowInputDev* sin = reinterpret_cast<RowInputDev*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev));
+  int* soff = reinterpret_cast<int*>(smem_raw + size_t(n_steps) * sizeof(RowStepDev) + size_t(n_inputs) * sizeof(RowInputDev));
+  float* tsm = reinterpret_cast<float*>(soff + ((off_ints + 3) & ~3));
+  for (int i = threadIdx.x; i < n_steps * int(sizeof(RowStepDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sst)[i] = reinterpret_cast<const uint32_t*>(steps)[i];
+  for (int i = threadIdx.x; i < n_inputs * int(sizeof(RowInputDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sin)[i] = reinterpret_cast<const uint32_t*>(inputs)[i];
+  for (int i = threadIdx.x; i < off_ints; i += blockDim.x) soff[i] = off_pool[i];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const float NEG_INF = __int_as_float(0xff800000);
+  for (int64_t row0 = int64_t(blockIdx.x) * ROWT_TPB; row0 < n_rows; row0 += int64_t(gridDim.x) * ROWT_TPB) {
+    const int64_t row = min(row0 + tid, n_rows - 1);       // threads past the end repeat the last row and do not store
+    bool bad = false;
+    for (int j = 0; j < n_steps; ++j) {
+      const RowStepDev& S = sst[j];
+      const float* gsrc[CBN_MAX_CONTRACT_INPUTS];
+      int tsrc[CBN_MAX_CONTRACT_INPUTS];
+#pragma unroll
+      for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
+        if (k < S.n_in) {
+          const int id = S.in_id[k];
+          if (id < n_inputs) {                               // static table: slice it by this row's evidence codes
+            const RowInputDev& I = sin[id];
+            int b = 0;
+            for (int a = 0; a < I.n_ev; ++a) {
+              const int c = ev[int64_t(I.slot[a]) * ld + row];
+              bad |= (c == CBN_UNSEEN);
+              b += c * I.stride[a];
+            }
+            gsrc[k] = I.data + (bad ? 0 : b);
+            tsrc[k] = -1;
+          } else {
+            gsrc[k] = nullptr;
+            tsrc[k] = sst[id - n_inputs].temp_off;
+          }
+        }
+      const int* offs = soff + S.off_at;
+      float mx;
+      switch (S.n_in) {
+        case 1: mx = rowt_step<LOG, 1>(S, offs, gsrc, tsrc, tsm, tid); break;
+        case 2: mx = rowt_step<LOG, 2>(S, offs, gsrc, tsrc, tsm, tid); break;
+        case 3: mx = rowt_step<LOG, 3>(S, offs, gsrc, tsrc, tsm, tid); break;
+        case 4: mx = rowt_step<LOG, 4>(S, offs, gsrc, tsrc, tsm, tid); break;
+        default: {
+          mx = LOG ? NEG_INF : 0.0f;
+          for (int o = 0; o < S.out_size; ++o) {
+            float acc = LOG ? NEG_INF : 0.0f;
+            for (int sv = 0; sv < S.sum_card; ++sv) {
+              float prod = LOG ? 0.0f : 1.0f;
+              for (int k = 0; k < S.n_in; ++k) {
+                const int idx = offs[k * S.out_size + o] + sv * S.sum_stride[k];
+                const float x = tsrc[k] < 0 ? __ldg(gsrc[k] + idx) : tsm[(tsrc[k] + idx) * ROWT_TPB + tid];
+                prod = LOG ? prod + x : prod * x;
+              }
+              acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
+            }
+            tsm[(S.temp_off + o) * ROWT_TPB + tid] = acc;
+            mx = fmaxf(mx, acc);
+          }
+        }
+      }
+      if (j + 1 < n_steps) {       // keep the temporary in range (a per-row constant cancels in the final normalisation)
+        if (LOG) {
+          if (mx != NEG_INF) for (int o = 0; o < S.out_size; ++o) tsm[(S.temp_off + o) * ROWT_TPB + tid] -= mx;
+        } else if (mx > 0.0f) {
+          const float inv = 1.0f / mx;
+          for (int o = 0; o < S.out_size; ++o) tsm[(S.temp_off + o) * ROWT_TPB + tid] *= inv;
+        }
+      }
+    }
+    // normalise the last temporary over the target and write the posterior row
+    const int last = sst[n_steps - 1].temp_off;
+    float z = 0.0f, mxl = NEG_INF;
+    if (LOG) for (int t = 0; t < card_t; ++t) mxl = fmaxf(mxl, tsm[(last + t) * ROWT_TPB + tid]);
+    for (int t = 0; t < card_t; ++t) {
+      const float v = tsm[(last + t) * ROWT_TPB + tid];
+      z += LOG ? (mxl == NEG_INF ? 0.0f : expf(v - mxl)) : v;
+    }
+    const float inv = (z > 0.0f && !bad) ? 1.0f / z : 0.0f;
+    if (row0 + tid < n_rows)
+      for (int t = 0; t < card_t; ++t) {
+        const float v = tsm[(last + t) * ROWT_TPB + tid];
+        out[row * card_t + t] = (LOG ? (mxl == NEG_INF ? 0.0f : expf(v - mxl)) : v) * inv;
+      }
+  }
+}
+}  // namespace
+
 extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                                        const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps,
                                        int32_t n_steps, int32_t flags, cbn_ve_plan** out) {
@@ -1281,7 +1422,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   }
   std::vector<RowStepDev> hs(n_steps);
   int temp = 0;
-  long long off_ints = 0;
+  long long off_ints = 0, terms = 0;       // terms = table / temporary reads per row
   for (int j = 0; j < n_steps; ++j) {
     const cbn_row_step& S = steps[j];
     if (S.out_size < 1 || S.sum_card < 1 || S.n_in < 1 || S.n_in > CBN_MAX_CONTRACT_INPUTS || !S.offsets)
@@ -1298,6 +1439,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
     }
     temp += (S.out_size + 3) & ~3;
     off_ints += (long long)S.n_in * S.out_size;
+    terms += (long long)S.n_in * S.out_size * S.sum_card;
   }
   if (steps[n_steps - 1].out_size != card_t)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: the last step must produce card_t cells");
@@ -1313,6 +1455,12 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
   p->rows_n_inputs = n_inputs; p->rows_n_steps = n_steps; p->rows_temp_floats = temp; p->rows_flags = flags;
   p->rows_off_ints = (int)off_ints;
+  // small schedules run one thread per row (see ve_rows_thread_kernel)
+  p->rows_thread_smem = size_t(n_steps) * sizeof(RowStepDev) + size_t(n_inputs) * sizeof(RowInputDev) + size_t((off_ints + 3) & ~3ll) * 4 +
+                        size_t(temp) * ROWT_TPB * 4;
+  // ... as long as the schedule is short: its table reads are per-thread gathers (one L1 sector each), which lose to the
+  // warp-per-row kernel's coalesced slice reads beyond a few hundred terms per row (measured, tools/exp_rows.py)
+  p->rows_per_thread = temp <= ROWT_MAX_TEMPS && terms <= ROWT_MAX_TERMS && p->rows_thread_smem <= 100 * 1024;
   p->blob_bytes = smem;
   cudaError_t e = cudaMalloc(&p->d_row_inputs, sizeof(RowInputDev) * n_inputs);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_row_inputs, hi.data(), sizeof(RowInputDev) * n_inputs, cudaMemcpyHostToDevice);
@@ -1324,12 +1472,30 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
     e = cudaMemcpy((int*)p->d_row_offsets + hs[j].off_at, steps[j].offsets, size_t(steps[j].n_in) * steps[j].out_size * 4, cudaMemcpyDeviceToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (e != cudaSuccess) { cbn_ve_plan_destroy(p); return cbn_fail(ctx, CBN_ERR_CUDA, "per-row plan upload: %s", cudaGetErrorString(e)); }
   *out = p;
   return CBN_OK;
 }
 
 static int ve_run_rows(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, float* out, cudaStream_t s) {
+  static int thread_mode = -1;
+  if (thread_mode < 0) { const char* e = getenv("CBN_ROWS_THREAD"); thread_mode = e ? atoi(e) : 1; }
+  if (p->rows_per_thread && thread_mode) {
+    const int per = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (p->rows_thread_smem + 1024)));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + ROWT_TPB - 1) / ROWT_TPB, int64_t(ctx->sm_count) * per));
+    if (p->rows_flags & CBN_ROWS_LOG_SPACE)
+      ve_rows_thread_kernel<true><<<blocks, ROWT_TPB, p->rows_thread_smem, s>>>(
+          (const RowInputDev*)p->d_row_inputs, p->rows_n_inputs, (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+          (const int*)p->d_row_offsets, p->rows_off_ints, ev, ld, n_rows, p->card_t, out);
+    else
+      ve_rows_thread_kernel<false><<<blocks, ROWT_TPB, p->rows_thread_smem, s>>>(
+          (const RowInputDev*)p->d_row_inputs, p->rows_n_inputs, (const RowStepDev*)p->d_row_steps, p->rows_n_steps, p->rows_temp_floats,
+          (const int*)p->d_row_offsets, p->rows_off_ints, ev, ld, n_rows, p->card_t, out);
+    CBN_CHECK_LAUNCH(ctx);
+    return CBN_OK;
+  }
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (p->blob_bytes + 1024)));
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + ROWS_WARPS - 1) / ROWS_WARPS, int64_t(ctx->sm_count) * per_sm));
   if (p->rows_flags & CBN_ROWS_LOG_SPACE)
