@@ -1088,9 +1088,10 @@ __device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* _
                                                int lane) {
   const float NEG_INF = __int_as_float(0xff800000);
   const float* src[NIN];
-  int ss[NIN];
+  long long sb[NIN];           // stride of the summed variable in elements: the running pointers advance by it (one
+                               // 64-bit add per term instead of re-deriving every address from a 32-bit index)
 #pragma unroll
-  for (int k = 0; k < NIN; ++k) { src[k] = srcs[k]; ss[k] = S.sum_stride[k]; }
+  for (int k = 0; k < NIN; ++k) { src[k] = srcs[k]; sb[k] = S.sum_stride[k]; }
   const int out_size = S.out_size, sum_card = S.sum_card;
   float mx = LOG ? NEG_INF : 0.0f;
   int o = lane;
@@ -1102,10 +1103,12 @@ __device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* _
     float a0 = LOG ? NEG_INF : 0.0f, a1 = a0;
 #pragma unroll 2
     for (int sv = 0; sv < sum_card; ++sv) {
-      float q0 = p0[0][sv * ss[0]], q1 = p1[0][sv * ss[0]];
+      float q0 = *p0[0], q1 = *p1[0];
+      p0[0] += sb[0]; p1[0] += sb[0];
 #pragma unroll
       for (int k = 1; k < NIN; ++k) {
-        const float x0 = p0[k][sv * ss[k]], x1 = p1[k][sv * ss[k]];
+        const float x0 = *p0[k], x1 = *p1[k];
+        p0[k] += sb[k]; p1[k] += sb[k];
         q0 = LOG ? q0 + x0 : q0 * x0;
         q1 = LOG ? q1 + x1 : q1 * x1;
       }
@@ -1122,10 +1125,12 @@ __device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* _
     float acc = LOG ? NEG_INF : 0.0f;
 #pragma unroll 4
     for (int sv = 0; sv < sum_card; ++sv) {
-      float prod = p[0][sv * ss[0]];
+      float prod = *p[0];
+      p[0] += sb[0];
 #pragma unroll
       for (int k = 1; k < NIN; ++k) {
-        const float x = p[k][sv * ss[k]];
+        const float x = *p[k];
+        p[k] += sb[k];
         prod = LOG ? prod + x : prod * x;
       }
       acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
@@ -1222,11 +1227,13 @@ __global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __
         __syncwarp();
         if (j + 1 < n_steps) {
           // keep the temporary in range: divide by its maximum (subtract it in log space)
+          const int n_out = S.out_size;      // a register copy: the stores below could alias the descriptor in shared memory
+          float* __restrict__ tp = tout + lane;
           if (LOG) {
-            if (mx != NEG_INF) for (int o = lane; o < S.out_size; o += 32) tout[o] -= mx;
+            if (mx != NEG_INF) for (int o = lane; o < n_out; o += 32, tp += 32) *tp -= mx;
           } else if (mx > 0.0f) {
             const float inv = 1.0f / mx;
-            for (int o = lane; o < S.out_size; o += 32) tout[o] *= inv;
+            for (int o = lane; o < n_out; o += 32, tp += 32) *tp *= inv;
           }
           __syncwarp();
         }
