@@ -377,23 +377,29 @@ def test_per_row_executor_matches_oracle():
             cols[3][5] = 1234.0
             got32 = plan.run_f32(cols, ev.shape[0]).cpu().numpy()
             assert np.array_equal(got32, got)
-    # naive-Bayes shape: one hidden cause with 40 observed children: the boundary (3^40) cannot be tabulated
-    rng = np.random.default_rng(12)
-    n_child = 40
-    names = ["cause", "t"] + [f"c{i:02d}" for i in range(n_child)]
-    cards = [4, 3] + [3] * n_child
-    parents = [[], [0]] + [[0]] * n_child
-    spec = synth.NetSpec(names, cards, parents, synth._dirichlet_cpts(rng, cards, parents, 0.5))
-    t = tables_from_spec(spec, DEV)
-    t.set_cond_tables(spec.cpts)
-    infer = bind_inference(t, table_budget_cells=1 << 16)
-    codes = synth.sample_forward_numpy(spec, 2, 0, 513)
-    evn = names[2:]
-    plan = infer.plan("t", evn)
-    assert isinstance(plan, RowPlan)
-    got = plan.run_codes(_codes_matrix(codes[2:].T), 513).cpu().numpy()
-    want = O.ve_posterior(_net(spec), 1, list(range(2, 2 + n_child)), codes[2:].T, dtype=torch.float64)
-    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+    # naive-Bayes shape: one hidden cause with many observed children: the boundary (3^40 / 3^24) cannot be tabulated.
+    # 40 children -> warp-per-row kernel, 24 children -> a short schedule, the one-thread-per-row kernel; both arithmetic modes
+    for n_child in (40, 24):
+        rng = np.random.default_rng(12)
+        names = ["cause", "t"] + [f"c{i:02d}" for i in range(n_child)]
+        cards = [4, 3] + [3] * n_child
+        parents = [[], [0]] + [[0]] * n_child
+        spec = synth.NetSpec(names, cards, parents, synth._dirichlet_cpts(rng, cards, parents, 0.5))
+        codes = synth.sample_forward_numpy(spec, 2, 0, 513)
+        evn = names[2:]
+        want = O.ve_posterior(_net(spec), 1, list(range(2, 2 + n_child)), codes[2:].T, dtype=torch.float64)
+        ev = codes[2:].T.copy()
+        ev[100, 7] = 255
+        for log_space in (False, True):
+            t = tables_from_spec(spec, DEV)
+            t.set_cond_tables(spec.cpts)
+            infer = bind_inference(t, table_budget_cells=1 << 16, log_space=log_space)
+            plan = infer.plan("t", evn)
+            assert isinstance(plan, RowPlan) and (plan.stats.per_row_madds <= 320) == (n_child == 24)
+            got = plan.run_codes(_codes_matrix(ev), 513).cpu().numpy()
+            ok = np.ones(513, bool); ok[100] = False
+            np.testing.assert_allclose(got[ok], want[ok], rtol=2e-5 if log_space else RTOL, atol=1e-30)
+            assert np.all(got[100] == 0)
 
 
 def test_fit_then_infer_end_to_end_on_fitted_tables():
