@@ -275,3 +275,32 @@ def test_host_code_matrix_counts_like_the_device_path():
     t = tables_from_spec(spec, DEV)
     t.count_host(host, 0)
     assert int(t.counts.sum()) == 0
+
+
+def test_multi_column_ingestion_beyond_one_launch_chunk():
+    """``cbn_domain_f32_multi`` / ``cbn_encode_f32_multi`` take 256 column pointers per launch: a 300-variable frame
+    goes through two chunks; domains, codes and the single-column entry points must agree with numpy."""
+    from continuousbayesiannetwork_b200.tables import DiscreteTables
+
+    rng = np.random.default_rng(21)
+    k, n = 300, 4099
+    names = [f"v{i:03d}" for i in range(k)]
+    cards = rng.integers(1, 9, size=k)
+    vals = [np.sort(rng.choice(np.arange(-40, 40) * 0.25, size=int(c), replace=False)).astype(np.float32) for c in cards]
+    data = np.stack([vals[i][rng.integers(0, cards[i], size=n)] for i in range(k)])          # [k, n]
+    cols = {nm: torch.tensor(data[i], device=DEV) for i, nm in enumerate(names)}
+    t = DiscreteTables(names, {}, device=DEV)
+    doms = t.discover_domains([cols[nm] for nm in names])
+    for i in range(k):
+        assert np.array_equal(doms[i].cpu().numpy(), np.unique(data[i])), i
+    t.set_domains(doms)
+    codes = t.encode_columns(cols)
+    want = np.stack([np.searchsorted(np.unique(data[i]), data[i]) for i in range(k)]).astype(np.uint8)
+    assert np.array_equal(codes[:, :n].cpu().numpy(), want)
+    one = torch.zeros(n + 16, dtype=torch.uint8, device=DEV)
+    t.encode(cols[names[299]], 299, one)
+    assert np.array_equal(one[:n].cpu().numpy(), want[299])
+    bad = dict(cols)
+    bad[names[257]] = cols[names[257]] + 1000.0
+    with pytest.raises(ValueError):
+        t.encode_columns(bad)
