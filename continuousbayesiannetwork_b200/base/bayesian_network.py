@@ -121,7 +121,8 @@ class BayesianNetwork:
         missing = [n for n in names if n not in data.columns]
         if missing:
             raise ValueError(f"data has no column for nodes {missing}")
-        block = np.ascontiguousarray(data[names].to_numpy(dtype=np.float32).T)      # [n_vars, n]
+        # [n_vars, n]; pandas hands out read-only views (copy-on-write): torch wants a writable, C-contiguous block
+        block = np.require(data[names].to_numpy(dtype=np.float32).T, requirements=["C", "W"])
         dev_block = torch.from_numpy(block).to(dev)
         return {n: dev_block[i] for i, n in enumerate(names)}
 
@@ -203,7 +204,7 @@ class BayesianNetwork:
         """Batched MAP prediction with every other column as evidence (reference :329-373).  The whole
         frame is one launch per ``batch_size`` rows; pass a large batch_size to do it in one."""
         feats = [f for f in data.columns if f != target_feature and f in self.nodes_obj]
-        block = torch.from_numpy(np.ascontiguousarray(data[feats].to_numpy(dtype=np.float32).T)).to(self.device)
+        block = torch.from_numpy(np.require(data[feats].to_numpy(dtype=np.float32).T, requirements=["C", "W"])).to(self.device)
         n = block.shape[1]
         pred = torch.empty(n, dtype=torch.float32, device=self.device)
         for s in range(0, n, batch_size):
