@@ -340,6 +340,7 @@ class VECompiler:
         self.log_space = bool(log_space)
         self._cache: Dict[tuple, QueryPlan] = {}
         self._has_zero: Dict[int, bool] = {}
+        self.last_row_schedule: Optional[dict] = None
 
     # ---------------------------------------------------------------- graph helpers
     def _parents(self, v: int) -> List[int]:
@@ -666,6 +667,10 @@ class VECompiler:
         while len(rf) > N.MAX_CONTRACT_INPUTS:
             rf = rf[N.MAX_CONTRACT_INPUTS:] + [emit(rf[:N.MAX_CONTRACT_INPUTS], [T], None)]
         emit(rf, [T], None)
+        # the schedule as plain host data (what cbn_ve_plan_create_rows receives): kept for inspection and for the
+        # CPU-side interpreter of tests/test_host_logic.py
+        self.last_row_schedule = {"target": T, "evidence": list(E), "static_scopes": [list(f.scope) for f in statics],
+                                  "steps": steps, "offsets": np.concatenate(off_chunks)}
         if dry:
             return None
         offsets = torch.from_numpy(np.concatenate(off_chunks)).to(self.t.device)

@@ -152,3 +152,58 @@ def test_incremental_greedy_matches_full_rescan():
             left.discard(v)
             nk += 1
         assert not g.hidden
+
+
+def test_row_schedule_interpreted_on_the_cpu_matches_the_oracle():
+    """The per-row elimination SCHEDULE (steps, offset tables, sum strides -- what ``cbn_ve_plan_create_rows`` receives) is
+    host logic: a numpy interpreter of it, fed with the ground-truth CPTs, must reproduce the oracle's posteriors.  A table
+    budget of one cell leaves every hidden variable to the per-row schedule."""
+    import torch
+
+    from oracle import cbn_oracle as O
+
+    rng = np.random.default_rng(3)
+    for spec, target, ev_names in ((synth.asia(), "lung", ["asia", "xray", "dysp"]),
+                                   (synth.random_ktree_dag(n=24, card=3, k=3, max_parents=2, seed=5), "x020", ["x003", "x011", "x017", "x023"])):
+        c = VECompiler(DryTables(spec.names, spec.cards, spec.parents_by_name()), table_budget_cells=1, row_temp_floats=1 << 22,
+                       check_support=False)
+        stats = c.compile(target, ev_names, dry=True)
+        assert stats.per_row_hidden > 0
+        sch = c.last_row_schedule
+        ev_ids = sch["evidence"]
+        assert ev_ids == [spec.names.index(e) for e in ev_names]
+        statics = []
+        for scope in sch["static_scopes"]:               # with a budget of 1 the static tables are the CPTs themselves
+            node = scope[-1]
+            assert scope == spec.parents[node] + [node]
+            statics.append((scope, np.asarray(spec.cpts[node], dtype=np.float64).reshape(-1)))
+        codes = synth.sample_forward_numpy(spec, 9, 0, 40)
+        rows = codes[ev_ids].T
+        got = np.zeros((rows.shape[0], spec.cards[sch["target"]]))
+        offs_all = sch["offsets"]
+        for r, ev in enumerate(rows):
+            code_of = dict(zip(ev_ids, ev))
+            bases = []
+            for scope, _ in statics:                      # slice every static table by the row's evidence codes
+                b, stride = 0, 1
+                for v in reversed(scope):
+                    if v in code_of:
+                        b += int(code_of[v]) * stride
+                    stride *= spec.cards[v]
+                bases.append(b)
+            temps = []
+            for st in sch["steps"]:
+                n_in, out_size = len(st["in_id"]), st["out_size"]
+                offs = offs_all[st["offsets_at"]: st["offsets_at"] + n_in * out_size].reshape(n_in, out_size)
+                out = np.zeros(out_size)
+                for o in range(out_size):
+                    for sv in range(st["sum_card"]):
+                        prod = 1.0
+                        for k, i in enumerate(st["in_id"]):
+                            idx = int(offs[k, o]) + sv * st["sum_stride"][k]
+                            prod *= statics[i][1][bases[i] + idx] if i < len(statics) else temps[i - len(statics)][idx]
+                        out[o] += prod
+                temps.append(out)
+            got[r] = temps[-1] / temps[-1].sum()
+        want = O.ve_posterior(O.DiscreteNet(spec.cards, spec.parents, spec.cpts), sch["target"], ev_ids, rows, dtype=torch.float64)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
