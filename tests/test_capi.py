@@ -37,11 +37,12 @@ def test_every_declared_symbol_is_exported_and_bound(native):
 
 def test_struct_layouts_match_the_header(native, tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "cbn_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(cbn_family), sizeof(cbn_contract), sizeof(cbn_gather_table));return 0;}\n')
+    prog.write_text('#include <stdio.h>\n#include "cbn_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(cbn_family), sizeof(cbn_contract), sizeof(cbn_gather_table), sizeof(cbn_row_input), sizeof(cbn_row_step));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(native.Family), C.sizeof(native.Contract), C.sizeof(native.GatherTable)]
+    assert sizes == [C.sizeof(native.Family), C.sizeof(native.Contract), C.sizeof(native.GatherTable), C.sizeof(native.RowInput),
+                     C.sizeof(native.RowStep)]
 
 
 def test_errors_without_a_gpu_are_loud(native):
