@@ -1,4 +1,4 @@
-"""Variable-elimination compiler: (target, evidence set) -> gather plan.
+"""Variable-elimination compiler: (target, evidence set) -> gather plan or per-row elimination plan.
 
 The reference has no working VE (cbn/inference/exact.py:13-14 is ``pass``; its
 ``BayesianNetwork.infer``, cbn/base/bayesian_network.py:208-305, is a posterior only
@@ -11,8 +11,14 @@ free axes of the factors ("evidence-symbolic" elimination).  What is left is a h
 of tables over (evidence subset, target); each query row only gathers one slice per
 table, multiplies and normalises -- an HBM-bound kernel (``cbn_ve_run_*``).
 
-Host work here is graph logic only (pruning, ordering, stride bookkeeping); every
-floating-point operation runs in ``cbn_factor_contract`` on the device.
+When the evidence boundary of the target's component is too large to tabulate (the cheapest
+remaining elimination step exceeds the table budget), compile-time elimination stops and the rest
+of the hidden variables is eliminated per row by a schedule of product / sum-out steps
+(``RowPlan`` -> ``cbn_ve_plan_create_rows``; linear space with per-step rescaling or log-sum-exp).
+
+Host work here is graph logic only (pruning, ordering with incremental bookkeeping, stride and
+offset tables); every floating-point operation runs on the device (``cbn_factor_contract`` at
+compile time, the gather / per-row kernels per evidence row).
 """
 from __future__ import annotations
 
