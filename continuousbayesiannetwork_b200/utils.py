@@ -1,23 +1,24 @@
-"""Factories keyed by the same config names as the reference (cbn/utils.py:23-38)."""
-from typing import Dict
+"""Factories keyed by the config names the reference uses (``estimator_name``, ``inference_obj``;
+cbn/utils.py:23-38).  An unknown name is a ``ValueError``, as in the reference; its inference factory is a no-op that
+returns ``None`` (:35-38), here it builds the engine."""
+from typing import Any, Dict, Mapping
 
-from .base.parameter_learning import BaseParameterLearningEstimator
+
+def _build(kind: str, registry: Mapping[str, type], name: str, config: Dict[str, Any], kwargs: Dict[str, Any]):
+    try:
+        cls = registry[name]
+    except KeyError:
+        raise ValueError(f"Unknown {kind}: {name}") from None
+    return cls(config, **kwargs)
 
 
-def choose_probability_estimator(estimator_name: str, config: Dict, **kwargs) -> BaseParameterLearningEstimator:
+def choose_probability_estimator(estimator_name: str, config: Dict[str, Any], **kwargs: Any):
     from .parameter_learning import ESTIMATORS
 
-    if estimator_name in ESTIMATORS.keys():
-        estimator_class = ESTIMATORS[estimator_name](config, **kwargs)
-    else:
-        raise ValueError(f"Unknown estimator: {estimator_name}")
-    return estimator_class
+    return _build("estimator", ESTIMATORS, estimator_name, config, kwargs)
 
 
-def choose_inference_obj(inference_name: str, config: Dict, **kwargs):
-    """The reference's factory is a no-op returning None (cbn/utils.py:35-38); here it builds the engine."""
+def choose_inference_obj(inference_name: str, config: Dict[str, Any], **kwargs: Any):
     from .inference import INFERENCE_OBJS
 
-    if inference_name in INFERENCE_OBJS.keys():
-        return INFERENCE_OBJS[inference_name](config, **kwargs)
-    raise ValueError(f"Unknown inference object: {inference_name}")
+    return _build("inference object", INFERENCE_OBJS, inference_name, config, kwargs)
