@@ -304,3 +304,35 @@ def test_multi_column_ingestion_beyond_one_launch_chunk():
     bad[names[257]] = cols[names[257]] + 1000.0
     with pytest.raises(ValueError):
         t.encode_columns(bad)
+
+
+def test_full_size_counting_properties():
+    """At the bench's sample counts the oracle is too slow; size-independent properties instead: every family table sums
+    to n, families that share a variable agree on its marginal, two half-passes add up to the full pass (linearity), and
+    the 512-thread and 256-thread kernels (200-node and Alarm plans) obey the same checks."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import sample_network, tables_from_spec
+
+    for spec, n in ((synth.asia(), 1 << 26), (synth.alarm(), 1 << 24), (synth.random_ktree_dag(), 1 << 22)):
+        codes = sample_network(spec, seed=23, first=0, n=n + 5, device=DEV)
+        n_odd = n + 5                                         # a ragged tail behind the last tile
+        t = tables_from_spec(spec, DEV)
+        t.count(codes, n_odd)
+        marg = {}
+        for i, name in enumerate(spec.names):
+            tab = t.table_view(t.counts, name)
+            assert int(tab.sum()) == n_odd, name
+            fam = spec.parents[i] + [i]
+            for ax, v in enumerate(fam):
+                m = tab.sum(dim=[d for d in range(tab.dim()) if d != ax]) if tab.dim() > 1 else tab
+                if v in marg:
+                    assert torch.equal(marg[v], m), (name, spec.names[v])
+                else:
+                    marg[v] = m
+        half = (n_odd // 2) // 16 * 16
+        a, b = tables_from_spec(spec, DEV), tables_from_spec(spec, DEV)
+        a.count(codes, half)
+        b.count(codes[:, half:], n_odd - half)
+        assert torch.equal(a.counts + b.counts, t.counts)
+        del codes, t, a, b
+        torch.cuda.empty_cache()

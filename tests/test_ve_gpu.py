@@ -422,3 +422,34 @@ def test_fit_then_infer_end_to_end_on_fitted_tables():
         got = infer.plan(target, ev_names).run_codes(_codes_matrix(ev), 4096).cpu().numpy()
         want = O.ve_posterior(net, spec.names.index(target), ids, ev)
         np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+
+
+def test_full_size_query_properties():
+    """BASELINE.json sizes (16,777,216 Alarm rows, 4 fused targets; 1,048,576 Asia rows, 3 fused targets): every posterior
+    row is a distribution, rows with identical evidence have bit-identical posteriors, the fused launch equals the
+    single-target plans, and a permutation of the rows permutes the posteriors."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts, sample_network
+
+    for spec, evn, targets, n in ((synth.alarm(), synth.ALARM_EVIDENCE, synth.ALARM_TARGETS, 1 << 24),
+                                  (synth.asia(), ["asia", "smoke", "xray", "dysp"], ["lung", "tub", "bronc"], 1 << 20)):
+        t, infer = install_cpts(spec, DEV)
+        ids = [spec.names.index(e) for e in evn]
+        ev = sample_network(spec, seed=31, first=0, n=n, device=DEV, tables=t)[ids].contiguous()
+        fused = infer.fused_plan(targets, evn)
+        outs = fused.run_codes(ev, n)
+        key = torch.zeros(n, dtype=torch.int64, device=DEV)
+        for i, v in enumerate(ids):
+            key = key * spec.cards[v] + ev[i, :n].long()
+        _, inv = torch.unique(key, return_inverse=True)
+        first = torch.full((int(inv.max()) + 1,), n, dtype=torch.int64, device=DEV).scatter_reduce(0, inv, torch.arange(n, device=DEV), "amin")
+        perm = torch.randperm(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+        ev_p = ev[:, perm].contiguous()
+        outs_p = fused.run_codes(ev_p, n)
+        for tg, o, op in zip(targets, outs, outs_p):
+            assert float((o.sum(1) - 1).abs().max()) < 1e-5
+            assert torch.equal(o, o[first[inv]])                                   # same evidence -> same posterior
+            assert torch.equal(op, o[perm])                                        # row order does not matter
+            assert torch.equal(infer.plan(tg, evn).run_codes(ev, n), o)            # fused == single
+        del outs, outs_p, ev, ev_p, key, inv, first, perm
+        torch.cuda.empty_cache()
