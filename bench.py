@@ -9,8 +9,11 @@ evidence {asia, smoke, xray, dysp} drawn from the joint, targets lung / tub / br
 compiled plans run over one batch of evidence rows; one *query* = one posterior row of one target.
 Inputs are device resident for `value`; `e2e` runs the same step through the C-ABI host-buffer call
 (pinned host codes in, pinned host posteriors out, copies inside the timed region).
-Between timed iterations the step rotates through a ring of distinct batches larger than L2.
-Prints ONE JSON line on rank 0.
+Between timed iterations the step rotates through a ring of distinct batches larger than L2; the K timed steps are
+ONE CUDA graph launch (kernels of consecutive steps spread over 3 streams inside the graph), `roofline.one_stream`
+reports the same launches as one graph on a single stream.
+Extra keys carry the other configurations: `fit` / `fit_e2e` / `ingest_fit_f32` (CPT counting), `alarm`, `alarm_fit`,
+`ktree200_fit`, `ktree200_ve`, `layered1000_ve` (BASELINE.json configs 3-5).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
