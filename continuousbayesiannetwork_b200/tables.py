@@ -49,6 +49,7 @@ class DiscreteTables:
         self._count_plan = None
         self._dom_matrix = None
         self._layout_cards: Optional[List[int]] = None
+        self._discovered = None
         self._counts_buf: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ layout
@@ -177,7 +178,8 @@ class DiscreteTables:
                 raise ValueError(
                     f"column {i} has more than {N.MAX_CARD} distinct values; it is not a discrete variable for the "
                     "brute-force estimator")
-        return [dom[i, :c].clone() for i, c in enumerate(cards)]
+        self._discovered = (dom, card, cards)        # fit_columns adopts the device matrix as it is (no second round trip)
+        return [dom[i, :c] for i, c in enumerate(cards)]
 
     def encode(self, col: torch.Tensor, var: int, out: torch.Tensor, unseen: Optional[torch.Tensor] = None):
         col = col.to(self.device, torch.float32).contiguous()
@@ -276,8 +278,11 @@ class DiscreteTables:
 
     def fit_columns(self, cols: Dict[str, torch.Tensor]):
         """Full fit from float32 columns: domains, codes, counts, CPTs."""
-        self.set_domains(self.discover_domains([cols[n].reshape(-1) for n in self.names]))
-        codes = self.encode_columns(cols)
+        doms = self.discover_domains([cols[n].reshape(-1) for n in self.names])
+        dom, card, _ = self._discovered
+        self.set_domains(doms)
+        self._dom_matrix = (dom, card)               # rows are zero-padded beyond the cardinality by the finish kernel
+        codes = self.encode_columns(cols, strict=False)   # every value is in the domain that was just built from it
         n = int(next(iter(cols.values())).numel())
         self.count(codes, n)
         self.finalize()
