@@ -136,6 +136,9 @@ static_assert(sizeof(GTable) % 16 == 0, "GTable is copied with 128-bit loads");
 struct GatherOuts {
   float* out[GATHER_MAX_OUT];
   unsigned normalize_mask;
+  // MAP mode (single-target plans): instead of the posterior row, store the domain value of its largest entry in
+  // out[0][row] (first maximum on ties, like argmax; an all-zero row gives the first domain value)
+  const float* map_domain;
 };
 }  // namespace
 
@@ -296,6 +299,40 @@ __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bo
   }
 }
 
+// MAP epilogue: one float per row (BayesianNetwork.benchmarking_df, bayesian_network.py:357-366, fused into the query)
+template <int CT>
+__device__ __forceinline__ void finish_map4(float (&p)[4][CT], uint32_t bad, int64_t quad, int64_t n_rows,
+                                            const float* __restrict__ dom, float* __restrict__ out) {
+  pdl_wait();
+  float v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int best = 0;
+    float pb = ((bad >> r) & 1u) ? 0.0f : p[r][0];
+#pragma unroll
+    for (int t = 1; t < CT; ++t) {
+      const float x = ((bad >> r) & 1u) ? 0.0f : p[r][t];
+      if (x > pb) { pb = x; best = t; }
+    }
+    v[r] = __ldg(dom + best);
+  }
+  const int64_t row0 = quad << 2;
+  if (row0 + 4 <= n_rows && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    st_na_f128(reinterpret_cast<float4*>(out + row0), make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (row0 + r < n_rows) out[row0 + r] = v[r];
+  }
+}
+
+template <int CT>
+__device__ __forceinline__ void finish_any4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad, int64_t n_rows,
+                                            const GatherOuts& outs, int which, uint64_t st_pol) {
+  if (outs.map_domain) finish_map4<CT>(p, bad, quad, n_rows, outs.map_domain, outs.out[which]);
+  else finish_rows4<CT>(p, bad, normalize, quad, n_rows, outs.out[which], st_pol);
+}
+
 // exact 32-bit index + unseen flags of one table for 4 rows (used when a code >= 128 shows up)
 template <typename Loader>
 __device__ __noinline__ uint4 exact_index4(const GTable& T, const Loader& L, int64_t quad, uint32_t lim, uint32_t* bad_out) {
@@ -325,7 +362,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
     const GTable& T = st[k];
     const int flags = T.flags;
     if (T.out_id != cur) {
-      if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur], st_pol);
+      if (cur >= 0) finish_any4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs, cur, st_pol);
       cur = T.out_id;
       bad = 0;
 #pragma unroll
@@ -399,7 +436,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       }
     }
   }
-  if (cur >= 0) finish_rows4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs.out[cur], st_pol);
+  if (cur >= 0) finish_any4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs, cur, st_pol);
 }
 
 // one straight 128-bit copy of the plan blob (descriptors + staged tables) into shared memory
@@ -1571,6 +1608,65 @@ extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float
   GatherOuts outs{};
   outs.out[0] = posterior;
   outs.normalize_mask = plan->normalize_mask;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (plan->card_t) {
+    case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 2: return launch_f32<2>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 3: return launch_f32<3>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 4: return launch_f32<4>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 5: return launch_f32<5>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 6: return launch_f32<6>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    case 7: return launch_f32<7>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+    default: return launch_f32<8>(ctx, plan, evp, dom_floats, n_rows, outs, s);
+  }
+}
+
+// ---- MAP value per row (fused posterior + argmax + domain lookup) ------------------------------------------------------
+static int check_map_plan(cbn_ctx* ctx, const char* fn, const cbn_ve_plan* plan, const float* target_domain, float* map_out, int64_t n_rows) {
+  if (!plan || n_rows < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
+  if (plan->kind != 0 || plan->n_out != 1 || plan->card_t > GATHER_MAX_CT)
+    return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "%s: needs a single-target gather plan with at most %d target values", fn, GATHER_MAX_CT);
+  if (n_rows > 0 && (!target_domain || !map_out)) return cbn_fail(ctx, CBN_ERR_INVALID, "%s: bad argument", fn);
+  return CBN_OK;
+}
+
+extern "C" int cbn_ve_run_codes_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
+                                    const float* target_domain, float* map_out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_map: ctx is NULL");
+  int rc = check_map_plan(ctx, "cbn_ve_run_codes_map", plan, target_domain, map_out, n_rows);
+  if (rc) return rc;
+  if (n_rows == 0) return CBN_OK;
+  if (plan->n_evidence > 0 && (!ev_codes || ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_map: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base");
+  DeviceGuard g(ctx->device);
+  GatherOuts outs{};
+  outs.out[0] = map_out;
+  outs.normalize_mask = 0;                 // the largest entry is the same with or without normalisation
+  outs.map_domain = target_domain;
+  return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, outs, (cudaStream_t)stream);
+}
+
+extern "C" int cbn_ve_run_f32_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols, const float* const* domains,
+                                  int64_t n_rows, const float* target_domain, float* map_out, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_f32_map: ctx is NULL");
+  int rc = check_map_plan(ctx, "cbn_ve_run_f32_map", plan, target_domain, map_out, n_rows);
+  if (rc) return rc;
+  if (n_rows == 0) return CBN_OK;
+  if (plan->n_evidence > 0 && (!ev_cols || !domains)) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32_map: bad argument");
+  if (plan->n_evidence > CBN_MAX_EVIDENCE_PTRS)
+    return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_run_f32_map: more than %d evidence columns; encode them and use cbn_ve_run_codes_map", CBN_MAX_EVIDENCE_PTRS);
+  DeviceGuard g(ctx->device);
+  EvPtrs evp{};
+  size_t dom_floats = 0;
+  for (int e = 0; e < plan->n_evidence; ++e) {
+    if (!ev_cols[e] || !domains[e]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_f32_map: evidence column %d is NULL", e);
+    evp.col[e] = ev_cols[e]; evp.dom[e] = domains[e]; evp.card[e] = plan->ev_cards[e];
+    dom_floats += plan->ev_cards[e];
+  }
+  GatherOuts outs{};
+  outs.out[0] = map_out;
+  outs.normalize_mask = 0;
+  outs.map_domain = target_domain;
   cudaStream_t s = (cudaStream_t)stream;
   switch (plan->card_t) {
     case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, outs, s);

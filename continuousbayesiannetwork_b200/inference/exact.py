@@ -79,6 +79,27 @@ class ExactInference(BaseInference):
                     out[chunk[0]] = plans[i].run_codes(codes, nq)
         return out
 
+    def infer_map(self, target_node: str, evidence: Dict[str, torch.Tensor]) -> Optional[torch.Tensor]:
+        """MAP value of the target per row through the fused kernel (``cbn_ve_run_f32_map``); ``None`` when the plan is
+        not a single-target gather plan with at most 8 target values (the caller then takes posterior + argmax)."""
+        t = self.tables
+        evidence = evidence or {}
+        names = [n for n in evidence.keys() if n != target_node]
+        for n in names:
+            if n not in t.index:
+                raise ValueError(f"evidence variable {n} is not a node of the network")
+        plan = self.plan(target_node, names)
+        if not isinstance(plan, QueryPlan) or plan.card_t > 8 or len(names) > 64:
+            return None
+        nq = int(evidence[names[0]].shape[0]) if names else 1
+        cols = []
+        for n in names:
+            c = evidence[n]
+            if c.shape[0] != nq:
+                raise ValueError("n_queries must be equal for all features.")
+            cols.append(c.to(t.device, torch.float32, non_blocking=True).reshape(-1).contiguous())
+        return plan.run_f32_map(cols, nq)
+
     def _infer(self, target_node: str, evidence: Dict[str, torch.Tensor], do=None, **kwargs) -> torch.Tensor:
         """Posterior ``P(target | evidence)`` per row: float32 [n_queries, card(target)] on the device.
 

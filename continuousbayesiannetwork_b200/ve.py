@@ -130,6 +130,27 @@ class QueryPlan:
                                        N.stream_ptr(self.device)), self.ctx.handle)
         return out
 
+    # MAP value per row: posterior + argmax + domain lookup fused into the query kernel (one float per row instead of a
+    # posterior row that a second kernel would read again)
+    def run_codes_map(self, ev_codes: torch.Tensor, n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(n_rows, dtype=torch.float32, device=self.device)
+        ld = ev_codes.stride(0) if ev_codes.dim() == 2 else 0
+        N.check(N.lib().cbn_ve_run_codes_map(self.ctx.handle, self.handle, ev_codes.data_ptr(), ld, int(n_rows),
+                                             self.owner.domains[self.target].data_ptr(), out.data_ptr(), N.stream_ptr(self.device)),
+                self.ctx.handle)
+        return out
+
+    def run_f32_map(self, ev_cols: Sequence[torch.Tensor], n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(n_rows, dtype=torch.float32, device=self.device)
+        cols = N.ptr_array([c.data_ptr() for c in ev_cols])
+        doms = N.ptr_array([self.owner.domains[v].data_ptr() for v in self.evidence])
+        N.check(N.lib().cbn_ve_run_f32_map(self.ctx.handle, self.handle, cols, doms, int(n_rows),
+                                           self.owner.domains[self.target].data_ptr(), out.data_ptr(), N.stream_ptr(self.device)),
+                self.ctx.handle)
+        return out
+
     def run_codes_host(self, ev_codes_host: torch.Tensor, n_rows: int, out_host: torch.Tensor) -> torch.Tensor:
         """Host buffers in, host buffer out (copies inside; synchronous)."""
         assert not ev_codes_host.is_cuda and not out_host.is_cuda

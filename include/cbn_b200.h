@@ -247,6 +247,15 @@ CBN_API int cbn_ve_run_codes_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const 
  * against the sorted domains.  ev_cols / domains: host arrays of device pointers. */
 CBN_API int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols,
                    const float* const* domains, int64_t n_rows, float* posterior, cbn_stream stream);
+
+/* MAP value per row -- the posterior, its argmax and the lookup of the target's domain value fused into the query kernel
+ * (BayesianNetwork.benchmarking_df, bayesian_network.py:329-373): map_out[row] = target_domain[argmax_t P(t | evidence_row)]
+ * (first maximum on ties; rows with an unseen or zero-probability evidence give target_domain[0]).  Single-target gather
+ * plans with at most 8 target values; map_out: device float [n_rows]; target_domain: device float [card_t]. */
+CBN_API int cbn_ve_run_codes_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes, int64_t ld, int64_t n_rows,
+                         const float* target_domain, float* map_out, cbn_stream stream);
+CBN_API int cbn_ve_run_f32_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const float* const* ev_cols, const float* const* domains,
+                       int64_t n_rows, const float* target_domain, float* map_out, cbn_stream stream);
 /* same as cbn_ve_run_codes but with HOST buffers (pinned or pageable): chunks are
  * copied in, processed and copied out on internal streams, double-buffered.
  * Synchronous: returns when `posterior_host` is complete. */

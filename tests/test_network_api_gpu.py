@@ -193,3 +193,39 @@ def test_infer_many_matches_infer_per_target():
         assert bool((pdf[5] == 0).all()) and abs(float(pdf[6].sum()) - 1) < 1e-5
     with pytest.raises(ValueError):
         bn.infer_many(["nope"], ev)
+
+
+def test_fused_map_matches_posterior_argmax(golden_dir):
+    """``infer_map`` / ``benchmarking_df`` use the fused MAP kernel (posterior + argmax + domain lookup in one launch):
+    same values as argmax over the posterior, on codes and on float evidence, including unseen evidence and a ragged tail."""
+    from continuousbayesiannetwork_b200 import BayesianNetwork, synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.alarm()
+    t, infer = install_cpts(spec, DEV)
+    n = 100_003
+    evn = synth.ALARM_EVIDENCE
+    ids = [spec.names.index(e) for e in evn]
+    rng = np.random.default_rng(4)
+    ev = np.stack([rng.integers(0, spec.cards[i], size=n) for i in ids], axis=1).astype(np.uint8)
+    ev[17, 2] = 255
+    ld = (n + 15) // 16 * 16
+    m = torch.zeros((len(ids), ld), dtype=torch.uint8, device=DEV)
+    m[:, :n] = torch.from_numpy(np.ascontiguousarray(ev.T)).to(DEV)
+    for target in ("VENTLUNG", "LVFAILURE", "CATECHOL"):
+        plan = infer.plan(target, evn)
+        post = plan.run_codes(m, n)
+        want = t.domains[spec.names.index(target)][post.argmax(dim=1)]
+        got = plan.run_codes_map(m, n)
+        assert torch.equal(got, want), target
+        cols = [m[i, :n].to(torch.float32) for i in range(len(ids))]
+        assert torch.equal(plan.run_f32_map(cols, n), want)
+    # through the network API on the FrozenLake fixture: benchmarking_df == argmax of infer
+    g, df, bn = _frozen_lake(golden_dir)
+    evd = {"obs_0": torch.tensor(df["obs_0"].to_numpy(dtype=np.float32)[:777, None]),
+           "action": torch.tensor(df["action"].to_numpy(dtype=np.float32)[:777, None])}
+    pdf, dom = bn.infer("reward", evd, N_max=16)
+    want = torch.gather(dom, 1, pdf.argmax(dim=1, keepdim=True)).squeeze(1)
+    assert torch.equal(bn.infer_map("reward", evd), want)
+    pred = bn.benchmarking_df(df.iloc[:777], "reward", batch_size=256)
+    assert np.array_equal(pred, want.cpu().numpy().astype(np.float64))
