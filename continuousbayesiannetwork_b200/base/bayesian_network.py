@@ -195,6 +195,31 @@ class BayesianNetwork:
             out[tn] = (pdf, dom.unsqueeze(0).expand(pdf.shape[0], -1))
         return out
 
+    def sample(self, N: int, seed: int = 0, first_sample: int = 0) -> Dict[str, torch.Tensor]:
+        """``N`` ancestral samples of the whole network from the fitted CPTs, as ``name -> float32 [N]`` device columns of
+        domain VALUES (the network analogue of the estimator's ``sample``, brute_force.py:246-265).  Counter-based: sample
+        ``first_sample + i`` depends only on ``(seed, first_sample + i)``, so any split of a range over calls or GPUs gives
+        the same data.  A parent configuration that was never observed has no distribution to draw from; the sampler then
+        returns the node's largest domain value."""
+        import ctypes as C
+
+        from .. import _native as NV
+
+        t = self.tables
+        if t.cond is None:
+            raise ValueError("the network is not fitted")
+        cdf = torch.empty_like(t.cond)
+        for i in range(len(t.names)):
+            card = t.cards[i]
+            seg = slice(t.offsets[i], t.offsets[i] + t.n_cells[i])
+            cdf[seg] = t.cond[seg].view(-1, card).cumsum(dim=1).reshape(-1)
+        order_names = list(nx.topological_sort(self.initial_dag))
+        order = (C.c_int32 * len(order_names))(*[t.index[self._node_name(n)] for n in order_names])
+        codes = t.new_code_matrix(int(N))
+        NV.check(NV.lib().cbn_sample_forward(t.ctx.handle, len(t.names), order, t.fams, cdf.data_ptr(), int(seed), int(first_sample),
+                                             int(N), codes.data_ptr(), codes.stride(0), NV.stream_ptr(t.device)), t.ctx.handle)
+        return {name: t.domains[i][codes[i, :N].long()] for i, name in enumerate(t.names)}
+
     def infer_map(self, target_node: str, evidence: Dict[str, torch.Tensor]) -> torch.Tensor:
         """MAP value of the target per row (what ``benchmarking_df`` extracts, :357-366)."""
         if target_node not in self.nodes_obj:

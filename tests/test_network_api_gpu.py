@@ -229,3 +229,29 @@ def test_fused_map_matches_posterior_argmax(golden_dir):
     assert torch.equal(bn.infer_map("reward", evd), want)
     pred = bn.benchmarking_df(df.iloc[:777], "reward", batch_size=256)
     assert np.array_equal(pred, want.cpu().numpy().astype(np.float64))
+
+
+def test_network_sampling_reproduces_the_fitted_distribution():
+    """``BayesianNetwork.sample``: ancestral samples from the fitted CPTs; a network re-fitted on them has the same CPTs up
+    to sampling noise, split ranges give the same data, values come from the fitted domains."""
+    from continuousbayesiannetwork_b200 import BayesianNetwork, synth
+
+    spec = synth.asia()
+    codes = synth.sample_forward_numpy(spec, 51, 0, 200_000)
+    df = pd.DataFrame({n: codes[i].astype(np.float32) * 2.0 + 1.0 for i, n in enumerate(spec.names)})      # values 1.0 / 3.0
+    dag = nx.DiGraph()
+    dag.add_nodes_from(spec.names)
+    dag.add_edges_from([(spec.names[p], spec.names[i]) for i in range(spec.n) for p in spec.parents[i]])
+    bn = BayesianNetwork(dag, df, PL, INF, device=DEV)
+    smp = bn.sample(400_000, seed=9)
+    assert set(smp) == set(spec.names) and all(v.shape == (400_000,) for v in smp.values())
+    assert all(set(torch.unique(v).tolist()) <= {1.0, 3.0} for v in smp.values())
+    a = bn.sample(1000, seed=9, first_sample=0)
+    b = bn.sample(600, seed=9, first_sample=400)
+    assert all(torch.equal(a[n][400:], b[n]) for n in spec.names)
+    bn2 = BayesianNetwork(dag, {n: v for n, v in smp.items()}, PL, INF, device=DEV)
+    for n in spec.names:
+        c1 = bn.tables.table_view(bn.tables.cond, n)
+        c2 = bn2.tables.table_view(bn2.tables.cond, n)
+        seen = bn2.tables.table_view(bn2.tables.counts, n).sum(-1) > 2000          # parent configurations with enough samples
+        assert float((c1 - c2)[seen].abs().max()) < 0.03, n
