@@ -259,8 +259,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def fit_step(_i):
-        big_tables.counts.zero_()
-        big_tables.n_total = 0
+        big_tables.reset_counts()
         sharding.fit_sharded(big_tables, big_codes, n_big)
 
     fit_steps = max(3, min(args.steps, 20))
@@ -562,8 +561,7 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
     torch.cuda.synchronize()
     barrier_t0 = time.perf_counter()
     for _ in range(3):
-        th.counts.zero_()
-        th.n_total = 0
+        th.reset_counts()
         th.count_host(hcodes, n_h)
         th.finalize()
     torch.cuda.synchronize()
@@ -618,8 +616,7 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
     torch.cuda.synchronize()
 
     def astep(_i):
-        ftab.counts.zero_()
-        ftab.n_total = 0
+        ftab.reset_counts()
         sharding.fit_sharded(ftab, codes, n_chunk)
 
     k = max(3, min(args.steps, 10))
@@ -638,8 +635,7 @@ def run_extras(args, dev, rank, world, timed, peak_gbs):
     torch.cuda.synchronize()
 
     def cstep(_i):
-        tables.counts.zero_()
-        tables.n_total = 0
+        tables.reset_counts()
         sharding.fit_sharded(tables, codes, n_chunk)
 
     k = max(3, min(args.steps, 5))

@@ -21,6 +21,7 @@ MAX_CONTRACT_DIMS = 24
 MAX_CONTRACT_INPUTS = 16
 MAX_GATHER_TABLES = 16
 MAX_EVIDENCE_PTRS = 64
+GATHER_MAX_CT = 8          # widest target the register-resident gather kernels (and the fused MAP epilogue) handle
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -101,7 +102,7 @@ SIGNATURES = {
     "cbn_count_plan_create": (C.c_int, [_P, C.POINTER(Family), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "cbn_count_plan_destroy": (None, [_P]),
     "cbn_count_run": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
-    "cbn_count_run_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "cbn_count_run_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "cbn_count_plan_groups": (C.c_int, [_P]),
     "cbn_count_plan_updates_per_sample": (C.c_int, [_P]),
     "cbn_cpt_from_counts": (C.c_int, [_P, _P, C.POINTER(Family), C.c_int32, C.c_longlong, _P, _P, _P]),
@@ -112,11 +113,12 @@ SIGNATURES = {
                                    C.c_int64, _P, _P]),
     "cbn_factor_contract": (C.c_int, [_P, C.POINTER(Contract), _P]),
     "cbn_ve_plan_create_gather": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(GatherTable),
-                                            C.c_int32, C.c_int32, C.POINTER(_P)]),
+                                            C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "cbn_ve_plan_create_rows": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(RowInput), C.c_int32,
-                                          C.POINTER(RowStep), C.c_int32, C.c_int32, C.POINTER(_P)]),
+                                          C.POINTER(RowStep), C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "cbn_ve_plan_destroy": (None, [_P]),
-    "cbn_ve_plan_fuse": (C.c_int, [_P, C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
+    "cbn_ve_plan_fuse": (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P, C.POINTER(_P)]),
+    "cbn_ve_plan_set_static_evidence": (C.c_int, [_P, C.c_int32]),
     "cbn_ve_plan_outputs": (C.c_int, [_P]),
     "cbn_ve_run_codes_multi": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P), _P]),
     "cbn_ve_run_codes": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
@@ -148,7 +150,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.cbn_abi_version() != 1:
+        if handle.cbn_abi_version() != 2:
             raise NativeLibraryMissing("libcbn_b200.so has an unexpected ABI version; rebuild it")
         _lib = handle
     return _lib

@@ -799,7 +799,7 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
 // host code matrix in, device count tables out: chunks of samples go H2D (one strided copy for all columns of a chunk)
 // on two alternating streams while the previous chunk is being counted; the tables accumulate as in cbn_count_run
 extern "C" int cbn_count_run_host(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes_host, int64_t ld, int64_t n,
-                                  unsigned long long* counts) {
+                                  unsigned long long* counts, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_count_run_host: ctx is NULL");
   if (!plan || n < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run_host: bad argument");
   if (n == 0) return CBN_OK;
@@ -826,9 +826,12 @@ extern "C" int cbn_count_run_host(cbn_ctx* ctx, const cbn_count_plan* plan, cons
   cudaPointerAttributes attr{};
   const bool pinned = cudaPointerGetAttributes(&attr, codes_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  // the counts may still be in use by work queued on the caller's stream: this entry point is synchronous, so order
-  // behind everything on the device first
-  CBN_CUDA(ctx, cudaDeviceSynchronize());
+  // the counts may still be in use by work queued on the caller's stream: the internal streams wait for an event
+  // recorded there (no device-wide synchronisation)
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->io_event[i]) CBN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->io_event[i], cudaEventDisableTiming));
+  CBN_CUDA(ctx, cudaEventRecord(ctx->io_event[0], (cudaStream_t)stream));
+  for (int i = 0; i < 2; ++i) CBN_CUDA(ctx, cudaStreamWaitEvent(ctx->io_stream[i], ctx->io_event[0], 0));
   int b = 0;
   for (int64_t s0 = 0; s0 < n; s0 += chunk, b ^= 1) {
     const int64_t m = std::min(chunk, n - s0);

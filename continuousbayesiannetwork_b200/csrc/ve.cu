@@ -167,6 +167,12 @@ struct cbn_ve_plan {
   size_t desc_bytes = 0;
   int staged = 0;
   long long table_bytes = 0;
+  // cbn_ve_plan_set_static_evidence: the evidence handed to runs of this plan is never written by the kernel that
+  // precedes the run on the stream, so the gather kernels may read it before griddepcontrol.wait
+  int static_evidence = 0;
+  // resident CTAs per SM of the kernel variant this plan launches ([0] direct, [1] tile-staged), queried once per plan
+  mutable int occ[2] = {0, 0};
+  mutable size_t occ_smem[2] = {0, 0};
 };
 
 namespace {
@@ -242,10 +248,13 @@ __device__ __forceinline__ void load_slice_l2(const float* __restrict__ src, flo
 }
 
 // Programmatic dependent launch: a gather kernel lets the next kernel of its stream start while it is still running
-// (pdl_trigger at entry) and only orders its own STORES behind the previous kernel (pdl_wait before the first store), so
-// back-to-back launches on one stream overlap their launch latency, prologue and evidence loads.  Both are no-ops for
-// launches without the programmatic-serialization attribute; a kernel that is not one of these never triggers early, so
-// ordinary stream order holds towards everybody else's kernels.
+// (pdl_trigger at entry).  The dependent kernel stages its plan blob (immutable after plan creation), then executes
+// griddepcontrol.wait BEFORE its first evidence load: the evidence may have been produced by the kernel right before it
+// (encode -> gather), and only the wait makes that kernel's writes visible.  A plan whose owner declares the evidence
+// static (cbn_ve_plan_set_static_evidence: resident batches replayed from a CUDA graph) defers the wait to just before the
+// first store, so evidence loads overlap the tail of the previous launch as well.  Both instructions are no-ops for launches
+// without the programmatic-serialization attribute; a kernel that is not one of these never triggers early, so ordinary
+// stream order holds towards everybody else's kernels.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -522,10 +531,11 @@ __device__ __forceinline__ void gather_inter_rows4(const GTable& T, const float*
 template <int CT, int NOUT>
 __global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
                                                                   int desc_bytes, const uint8_t* __restrict__ ev, int64_t ld,
-                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+                                                                  int64_t n_rows, int early_ev, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
+  if (!early_ev) pdl_wait();     // the evidence may have been written by the previous kernel of the stream
   const GTable& T = *reinterpret_cast<const GTable*>(smem_raw);
   const float* base = T.smem_off >= 0 ? reinterpret_cast<const float*>(smem_raw + desc_bytes) + T.smem_off : T.data;
   CodeLoader L{ev, ld};
@@ -558,11 +568,12 @@ template <int CT, int NOUT>     // NOUT == 0: generic table list (gather_rows4);
 __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
                                                                   int desc_bytes, int n_tables, const __grid_constant__ TileCols cols,
                                                                   int n_stages, int hints, const uint8_t* __restrict__ ev, int64_t ld,
-                                                                  int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+                                                                  int64_t n_rows, int early_ev, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
   pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
+  if (!early_ev) pdl_wait();     // the evidence may have been written by the previous kernel of the stream
   GTable* st = reinterpret_cast<GTable*>(smem_raw);
   // descriptors address evidence slots; inside this kernel they address staged tile columns
   for (int i = threadIdx.x; i < n_tables * GATHER_MAX_TABLE_EV; i += blockDim.x) {
@@ -641,10 +652,11 @@ constexpr int gather_min_blocks(int ct) { return ct <= 2 ? 6 : (ct <= 4 ? 5 : 3)
 template <int CT>
 __global__ void __launch_bounds__(GATHER_TPB, gather_min_blocks(CT)) gather_codes_kernel(
     const unsigned char* __restrict__ blob, int blob_bytes, int desc_bytes, int n_tables, const uint8_t* __restrict__ ev,
-    int64_t ld, int64_t n_rows, const __grid_constant__ GatherOuts outs) {
+    int64_t ld, int64_t n_rows, int early_ev, const __grid_constant__ GatherOuts outs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_trigger();
   stage_blob(blob, blob_bytes, smem_raw);
+  if (!early_ev) pdl_wait();     // the evidence may have been written by the previous kernel of the stream
   const GTable* st = reinterpret_cast<const GTable*>(smem_raw);
   const float* pool = reinterpret_cast<const float*>(smem_raw + desc_bytes);
   CodeLoader L{ev, ld};
@@ -723,8 +735,11 @@ bool same_index(const GTable& a, const GTable& b) {
   return true;
 }
 
-// lay the tables out for the kernel (shared-memory staging, index sharing, index arithmetic mode) and build the blob
-int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
+// lay the tables out for the kernel (shared-memory staging, index sharing, index arithmetic mode) and build the blob.
+// The uploads run on the caller's stream (behind the contraction kernels that produced the tables) and the function
+// returns after that stream has drained: from then on the blob is immutable, which is what allows a gather kernel to
+// stage it before griddepcontrol.wait.
+int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p, cudaStream_t s) {
   const int n = (int)p->h_tables.size();
   long long total_cells = 0;
   for (auto& t : p->h_tables) { total_cells += t.n_cells; t.smem_off = -1; }
@@ -737,7 +752,7 @@ int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
   }
   for (int k = 0; k < n; ++k) {
     GTable& t = p->h_tables[k];
-    long long reach = (t.flags & GT_HAS_TARGET) ? 0 : 0;
+    long long reach = 0;
     for (int j = 0; j < t.n_ev; ++j) reach += (long long)(p->ev_cards[t.slot[j]] - 1) * t.stride[j];
     const int mode = reach <= 255 ? 0 : (reach <= 65535 ? 1 : 2);
     t.flags = (t.flags & GT_HAS_TARGET) | (mode << GT_MODE_SHIFT);
@@ -749,13 +764,14 @@ int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
   p->table_bytes = total_cells * 4;
   if (p->d_blob) { cudaFree(p->d_blob); p->d_blob = nullptr; }
   cudaError_t e = cudaMalloc((void**)&p->d_blob, p->blob_bytes);
-  if (e == cudaSuccess) e = cudaMemset(p->d_blob, 0, p->blob_bytes);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, p->h_tables.data(), desc_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && p->blob_bytes > desc_bytes) e = cudaMemsetAsync(p->d_blob + desc_bytes, 0, p->blob_bytes - desc_bytes, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_blob, p->h_tables.data(), desc_bytes, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && p->staged)
     for (const auto& t : p->h_tables) {
-      e = cudaMemcpy(p->d_blob + desc_bytes + size_t(t.smem_off) * 4, t.data, size_t(t.n_cells) * 4, cudaMemcpyDeviceToDevice);
+      e = cudaMemcpyAsync(p->d_blob + desc_bytes + size_t(t.smem_off) * 4, t.data, size_t(t.n_cells) * 4, cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) break;
     }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return cbn_fail(ctx, CBN_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
   return CBN_OK;
 }
@@ -763,7 +779,7 @@ int finalize_plan(cbn_ctx* ctx, cbn_ve_plan* p) {
 
 extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                                          const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
-                                         cbn_ve_plan** out) {
+                                         cbn_stream stream, cbn_ve_plan** out) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: ctx is NULL");
   if (!out || n_evidence < 0 || n_evidence > 255 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD ||
       !tables || n_tables < 1 || n_tables > CBN_MAX_GATHER_TABLES)
@@ -799,13 +815,15 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
   p->n_out = 1; p->normalize_mask = normalize ? 1u : 0u;
   p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
   p->h_tables = h;
-  int rc = finalize_plan(ctx, p);
+  int rc = finalize_plan(ctx, p, (cudaStream_t)stream);
   if (rc) { cbn_ve_plan_destroy(p); return rc; }
   *out = p;
   return CBN_OK;
 }
 
-extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_ve_plan** out) {
+extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_stream stream,
+                                cbn_ve_plan** out) {
+  cudaStream_t cs = (cudaStream_t)stream;
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_fuse: ctx is NULL");
   if (!plans || !out || n_plans < 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: bad argument");
   DeviceGuard g(ctx->device);
@@ -844,8 +862,8 @@ extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, i
       const long long n_cfg = p->h_tables[0].n_cells / ct;
       cudaError_t e = cudaMalloc((void**)&p->d_inter, size_t(n_cfg) * w * sizeof(float));
       for (int k = 0; e == cudaSuccess && k < n_out; ++k)
-        e = cudaMemcpy2D(p->d_inter + k * ct, size_t(w) * sizeof(float), p->h_tables[k].data, size_t(ct) * sizeof(float),
-                         size_t(ct) * sizeof(float), size_t(n_cfg), cudaMemcpyDeviceToDevice);
+        e = cudaMemcpy2DAsync(p->d_inter + k * ct, size_t(w) * sizeof(float), p->h_tables[k].data, size_t(ct) * sizeof(float),
+                              size_t(ct) * sizeof(float), size_t(n_cfg), cudaMemcpyDeviceToDevice, cs);
       if (e != cudaSuccess) { cbn_ve_plan_destroy(p); return cbn_fail(ctx, CBN_ERR_CUDA, "interleave: %s", cudaGetErrorString(e)); }
       GTable t = p->h_tables[0];
       t.data = p->d_inter;
@@ -855,9 +873,15 @@ extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, i
       p->interleaved = n_out;
     }
   }
-  int rc = finalize_plan(ctx, p);
+  int rc = finalize_plan(ctx, p, cs);
   if (rc) { cbn_ve_plan_destroy(p); return rc; }
   *out = p;
+  return CBN_OK;
+}
+
+extern "C" int cbn_ve_plan_set_static_evidence(cbn_ve_plan* plan, int32_t on) {
+  if (!plan) return CBN_ERR_INVALID;
+  plan->static_evidence = on ? 1 : 0;
   return CBN_OK;
 }
 
@@ -906,15 +930,14 @@ int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     attr_set[ctx->device & 63] = true;
   }
   // one wave: as many CTAs as fit (register / shared-memory bound), the rest of the rows by the grid-stride loop
-  static size_t occ_smem = ~size_t(0);
-  static int occ = 1;
-  if (occ_smem != p->blob_bytes) {   // resident CTAs per SM for this shared-memory size (queried once)
+  if (p->occ[0] == 0 || p->occ_smem[0] != p->blob_bytes) {   // resident CTAs per SM for this plan (queried once)
+    int occ = 1;
     CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_codes_kernel<CT>, GATHER_TPB, p->blob_bytes));
-    occ_smem = p->blob_bytes;
+    p->occ[0] = std::max(occ, 1); p->occ_smem[0] = p->blob_bytes;
   }
-  const int per_sm = std::max(occ, 1);
+  const int per_sm = p->occ[0];
   CBN_CUDA(ctx, launch_pdl(gather_codes_kernel<CT>, gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s,
-                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, outs));
+                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, p->n_tables, ev, ld, n_rows, p->static_evidence, outs));
   return CBN_OK;
 }
 template <int CT>
@@ -941,15 +964,14 @@ int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_inter_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  static size_t occ_smem = ~size_t(0);
-  static int occ = 1;
-  if (occ_smem != p->blob_bytes) {   // resident CTAs per SM for this shared-memory size (queried once)
+  if (p->occ[0] == 0 || p->occ_smem[0] != p->blob_bytes) {   // resident CTAs per SM for this plan (queried once)
+    int occ = 1;
     CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_inter_kernel<CT, NOUT>, GATHER_TPB, p->blob_bytes));
-    occ_smem = p->blob_bytes;
+    p->occ[0] = std::max(occ, 1); p->occ_smem[0] = p->blob_bytes;
   }
-  const int per_sm = std::max(occ, 1);
+  const int per_sm = p->occ[0];
   CBN_CUDA(ctx, launch_pdl(gather_inter_kernel<CT, NOUT>, gather_blocks(ctx, n_rows, per_sm), GATHER_TPB, p->blob_bytes, s,
-                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, outs));
+                           p->d_blob, (int)p->blob_bytes, (int)p->desc_bytes, ev, ld, n_rows, p->static_evidence, outs));
   return CBN_OK;
 }
 
@@ -978,17 +1000,16 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
     CBN_CUDA(ctx, cudaFuncSetAttribute(gather_tiles_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[ctx->device & 63] = true;
   }
-  static size_t occ_smem = ~size_t(0);
-  static int occ = 1;
-  if (occ_smem != smem) {
+  if (p->occ[1] == 0 || p->occ_smem[1] != smem) {
+    int occ = 1;
     CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_tiles_kernel<CT, NOUT>, GATHER_TPB, smem));
-    occ_smem = smem;
+    p->occ[1] = std::max(occ, 1); p->occ_smem[1] = smem;
   }
   const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
-  const int per_sm = std::max(occ, 1);
+  const int per_sm = p->occ[1];
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, int64_t(ctx->sm_count) * per_sm));
   CBN_CUDA(ctx, launch_pdl(gather_tiles_kernel<CT, NOUT>, blocks, GATHER_TPB, smem, s, p->d_blob, (int)p->blob_bytes,
-                           (int)p->desc_bytes, p->n_tables, cols, n_stages, hints, ev, ld, n_rows, outs));
+                           (int)p->desc_bytes, p->n_tables, cols, n_stages, hints, ev, ld, n_rows, p->static_evidence, outs));
   return CBN_OK;
 }
 
@@ -1088,8 +1109,10 @@ struct RowInputDev {
   int n_cells;
   int n_ev;
   uint8_t slot[GATHER_MAX_TABLE_EV];
+  uint8_t card[GATHER_MAX_TABLE_EV];   // cardinality of the evidence variable behind slot[j]: a code >= card is treated as unseen
   int stride[GATHER_MAX_TABLE_EV];
 };
+static_assert(sizeof(RowInputDev) % 4 == 0, "RowInputDev is staged with 32-bit copies");
 struct RowStepDev {
   const int* offsets;
   int out_size, sum_card, n_in, temp_off;
@@ -1233,7 +1256,7 @@ __global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __
       int b = 0;
       for (int j = 0; j < I.n_ev; ++j) {
         const int c = codes[I.slot[j]];
-        bad |= (c == CBN_UNSEEN);
+        bad |= (c >= I.card[j]);          // CBN_UNSEEN or any code outside the domain: the row is all zeros
         b += c * I.stride[j];
       }
       base[k] = bad ? 0 : b;
@@ -1377,7 +1400,7 @@ __global__ void __launch_bounds__(ROWT_TPB) ve_rows_thread_kernel(const RowInput
             int b = 0;
             for (int a = 0; a < I.n_ev; ++a) {
               const int c = ev[int64_t(I.slot[a]) * ld + row];
-              bad |= (c == CBN_UNSEEN);
+              bad |= (c >= I.card[a]);      // CBN_UNSEEN or any code outside the domain: the row is all zeros
               b += c * I.stride[a];
             }
             gsrc[k] = I.data + (bad ? 0 : b);
@@ -1441,7 +1464,8 @@ __global__ void __launch_bounds__(ROWT_TPB) ve_rows_thread_kernel(const RowInput
 
 extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                                        const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps,
-                                       int32_t n_steps, int32_t flags, cbn_ve_plan** out) {
+                                       int32_t n_steps, int32_t flags, cbn_stream stream, cbn_ve_plan** out) {
+  cudaStream_t cs = (cudaStream_t)stream;
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: ctx is NULL");
   if (!out || n_evidence < 0 || n_evidence > 255 || (n_evidence > 0 && !ev_cards) || card_t < 1 || card_t > CBN_MAX_CARD ||
       !inputs || n_inputs < 1 || n_inputs > ROWS_MAX_INPUTS || !steps || n_steps < 1 || n_steps > ROWS_MAX_STEPS)
@@ -1459,6 +1483,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
       if (I.ev_slot[j] < 0 || I.ev_slot[j] >= n_evidence || I.ev_stride[j] < 0)
         return cbn_fail(ctx, CBN_ERR_INVALID, "row input %d: bad evidence axis %d", k, j);
       hi[k].slot[j] = (uint8_t)I.ev_slot[j];
+      hi[k].card[j] = (uint8_t)std::min(ev_cards[I.ev_slot[j]], 255);
       hi[k].stride[j] = I.ev_stride[j];
       reach += (long long)(ev_cards[I.ev_slot[j]] - 1) * I.ev_stride[j];
     }
@@ -1506,14 +1531,17 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   // warp-per-row kernel's coalesced slice reads beyond a few hundred terms per row (measured, tools/exp_rows.py)
   p->rows_per_thread = temp <= ROWT_MAX_TEMPS && terms <= ROWT_MAX_TERMS && p->rows_thread_smem <= 100 * 1024;
   p->blob_bytes = smem;
+  // uploads on the caller's stream (the offset tables and static inputs were produced there); one synchronisation at the end
   cudaError_t e = cudaMalloc(&p->d_row_inputs, sizeof(RowInputDev) * n_inputs);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_row_inputs, hi.data(), sizeof(RowInputDev) * n_inputs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_row_inputs, hi.data(), sizeof(RowInputDev) * n_inputs, cudaMemcpyHostToDevice, cs);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_row_steps, sizeof(RowStepDev) * n_steps);
-  if (e == cudaSuccess) e = cudaMemcpy(p->d_row_steps, hs.data(), sizeof(RowStepDev) * n_steps, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_row_steps, hs.data(), sizeof(RowStepDev) * n_steps, cudaMemcpyHostToDevice, cs);
   // the steps' offset tables, packed into one pool that the kernel stages in shared memory
   if (e == cudaSuccess) e = cudaMalloc(&p->d_row_offsets, size_t(std::max<long long>(off_ints, 1)) * 4);
   for (int j = 0; e == cudaSuccess && j < n_steps; ++j)
-    e = cudaMemcpy((int*)p->d_row_offsets + hs[j].off_at, steps[j].offsets, size_t(steps[j].n_in) * steps[j].out_size * 4, cudaMemcpyDeviceToDevice);
+    e = cudaMemcpyAsync((int*)p->d_row_offsets + hs[j].off_at, steps[j].offsets, size_t(steps[j].n_in) * steps[j].out_size * 4,
+                        cudaMemcpyDeviceToDevice, cs);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

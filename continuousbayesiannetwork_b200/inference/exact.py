@@ -5,6 +5,7 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
+from .. import _native as N
 from ..base.inference import BaseInference
 from ..ve import FusedPlan, QueryPlan, RowPlan, VECompiler
 
@@ -89,7 +90,7 @@ class ExactInference(BaseInference):
             if n not in t.index:
                 raise ValueError(f"evidence variable {n} is not a node of the network")
         plan = self.plan(target_node, names)
-        if not isinstance(plan, QueryPlan) or plan.card_t > 8 or len(names) > 64:
+        if not isinstance(plan, QueryPlan) or plan.card_t > N.GATHER_MAX_CT or len(names) > N.MAX_EVIDENCE_PTRS:
             return None
         nq = int(evidence[names[0]].shape[0]) if names else 1
         cols = []
@@ -125,8 +126,6 @@ class ExactInference(BaseInference):
         out = plan.run_f32(cols, nq)
         norm = kwargs.get("normalization", self.normalization)
         if norm == "global_max":
-            from .. import _native as N
-
             m = torch.zeros(1, dtype=torch.float32, device=t.device)
             s = N.stream_ptr(t.device)
             N.check(N.lib().cbn_batch_max(t.ctx.handle, out.data_ptr(), out.numel(), m.data_ptr(), s), t.ctx.handle)

@@ -50,10 +50,39 @@ def global_rows(local_rows: int, device=None) -> int:
 
 
 def fit_sharded(tables, codes: torch.Tensor, n_local: int):
-    """Count the local shard, all-reduce the tables, normalise with the GLOBAL sample count."""
+    """Count the local shard, all-reduce the tables, normalise with the GLOBAL sample count.
+
+    The first call on fresh tables reduces them in place.  After that the tables already hold the global counts, so a
+    further call (incremental / chunked ingest) counts its shard into a zeroed delta buffer, reduces the DELTA and adds
+    it: reducing the accumulated buffer again would multiply the earlier counts by the world size."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if multi and tables.is_reduced():
+        delta = tables.count_delta(codes, n_local)
+        allreduce_counts(delta)
+        tables.add_delta(delta)
+    else:
+        tables.count(codes, n_local)
+        if multi:
+            # tables and sample count travel together: one collective, no host synchronisation
+            allreduce_counts(tables.allreduce_buffer())
+            tables.mark_reduced()
+    tables.finalize()
+    return tables
+
+
+def count_local(tables, codes: torch.Tensor, n_local: int):
+    """Chunked ingest, phase 1: accumulate a local chunk WITHOUT communicating (call ``reduce_and_finalize`` once at the
+    end).  Must not be mixed with ``fit_sharded`` on tables that are already reduced."""
+    if tables.is_reduced():
+        raise RuntimeError("tables already hold global counts: use fit_sharded (delta reduction) for further chunks")
     tables.count(codes, n_local)
+
+
+def reduce_and_finalize(tables):
+    """Chunked ingest, phase 2: ONE all-reduce of everything counted locally so far, then the CPTs."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        # tables and sample count travel together: one collective, no host synchronisation
+        if tables.is_reduced():
+            raise RuntimeError("tables were already reduced")
         allreduce_counts(tables.allreduce_buffer())
         tables.mark_reduced()
     tables.finalize()

@@ -51,6 +51,7 @@ class DiscreteTables:
         self._layout_cards: Optional[List[int]] = None
         self._discovered = None
         self._counts_buf: Optional[torch.Tensor] = None
+        self._reduced = False            # the tables hold GLOBAL counts (summed over the ranks of a sharded fit)
 
     # ------------------------------------------------------------------ layout
     def set_domains(self, domains: Sequence[torch.Tensor]):
@@ -71,10 +72,9 @@ class DiscreteTables:
     def _layout(self):
         if self.fams is not None and self._layout_cards == self.cards and self._counts_buf is not None:
             # same structure and cardinalities as before (a re-fit): keep the tables' layout and the count plan
-            self._counts_buf.zero_()
+            self.reset_counts()
             self.joint = None
             self.cond = None
-            self._n_host, self._n_host_valid = 0, True
             return
         self._destroy_plan()
         self._layout_cards = list(self.cards)
@@ -103,6 +103,13 @@ class DiscreteTables:
         self.joint = None
         self.cond = None
         self._n_host, self._n_host_valid = 0, True
+        self._reduced = False
+
+    def reset_counts(self):
+        """Empty tables (and sample count) for a fresh fit; the layout and the count plan are kept."""
+        self._counts_buf.zero_()
+        self._n_host, self._n_host_valid = 0, True
+        self._reduced = False
 
     @property
     def n_total(self) -> int:
@@ -122,6 +129,26 @@ class DiscreteTables:
         return self._counts_buf
 
     def mark_reduced(self):
+        """The buffer now holds the sum over all ranks: later sharded calls must reduce only their own delta."""
+        self._n_host_valid = False
+        self._reduced = True
+
+    def is_reduced(self) -> bool:
+        return self._reduced
+
+    def count_delta(self, codes: torch.Tensor, n: int) -> torch.Tensor:
+        """Counts (and sample count) of ``n`` samples in a fresh zeroed buffer laid out like ``allreduce_buffer()``;
+        the tables themselves are not touched.  ``add_delta`` folds a (reduced) delta in."""
+        assert codes.dtype == torch.uint8 and codes.dim() == 2 and codes.shape[0] == len(self.names) and codes.stride(1) == 1
+        self._ensure_plan()
+        delta = torch.zeros_like(self._counts_buf)
+        N.check(N.lib().cbn_count_run(self.ctx.handle, self._count_plan, codes.data_ptr(), codes.stride(0), int(n),
+                                      delta.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
+        delta[self.total_cells] = int(n)
+        return delta
+
+    def add_delta(self, delta: torch.Tensor):
+        self._counts_buf.add_(delta)
         self._n_host_valid = False
 
     def _destroy_plan(self):
@@ -237,7 +264,7 @@ class DiscreteTables:
         assert not codes_host.is_cuda and codes_host.stride(1) == 1
         self._ensure_plan()
         N.check(N.lib().cbn_count_run_host(self.ctx.handle, self._count_plan, codes_host.data_ptr(), codes_host.stride(0), int(n),
-                                           self.counts.data_ptr()), self.ctx.handle)
+                                           self.counts.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
         self._n_dev.add_(int(n))
         if self._n_host_valid:
             self._n_host += int(n)

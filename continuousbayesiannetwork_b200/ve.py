@@ -95,7 +95,7 @@ class QueryPlan:
         ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
         h = C.c_void_p()
         N.check(N.lib().cbn_ve_plan_create_gather(self.ctx.handle, len(self.evidence), ev_cards, card_t, arr, len(finals),
-                                                  1 if normalize else 0, C.byref(h)), self.ctx.handle)
+                                                  1 if normalize else 0, N.stream_ptr(self.device), C.byref(h)), self.ctx.handle)
         self.handle = h
 
     def __del__(self):
@@ -120,8 +120,24 @@ class QueryPlan:
                                          out.data_ptr(), N.stream_ptr(self.device)), self.ctx.handle)
         return out
 
+    def set_static_evidence(self, on: bool = True):
+        """Declare that the evidence of this plan's runs is never written by the kernel preceding the run on the same
+        stream (resident batches replayed from a CUDA graph): evidence loads may then overlap the previous launch."""
+        N.check(N.lib().cbn_ve_plan_set_static_evidence(self.handle, 1 if on else 0), self.ctx.handle)
+
+    def _encode_evidence(self, ev_cols: Sequence[torch.Tensor], n_rows: int) -> torch.Tensor:
+        ld = (max(n_rows, 1) + 15) // 16 * 16
+        codes = torch.empty((max(len(self.evidence), 1), ld), dtype=torch.uint8, device=self.device)
+        for e, (v, col) in enumerate(zip(self.evidence, ev_cols)):
+            self.owner.encode(col, v, codes[e])
+        return codes
+
     def run_f32(self, ev_cols: Sequence[torch.Tensor], n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ev_cols[e]: float32 device column of evidence variable e (the reference's [nq,1] tensors)."""
+        if self.card_t > N.GATHER_MAX_CT or len(self.evidence) > N.MAX_EVIDENCE_PTRS:
+            # wide targets / very many evidence columns: the float kernel keeps the posterior in registers and takes its
+            # column pointers as kernel arguments; encode on the device and use the code kernels (any cardinality)
+            return self.run_codes(self._encode_evidence(ev_cols, n_rows), n_rows, out)
         if out is None:
             out = torch.empty((n_rows, self.card_t), dtype=torch.float32, device=self.device)
         cols = N.ptr_array([c.data_ptr() for c in ev_cols])
@@ -171,7 +187,7 @@ class FusedPlan:
         self.card_t = plans[0].card_t
         arr = N.ptr_array([p.handle.value for p in plans])
         h = C.c_void_p()
-        N.check(N.lib().cbn_ve_plan_fuse(self.ctx.handle, arr, len(plans), C.byref(h)), self.ctx.handle)
+        N.check(N.lib().cbn_ve_plan_fuse(self.ctx.handle, arr, len(plans), N.stream_ptr(self.device), C.byref(h)), self.ctx.handle)
         self.handle = h
         self.n_out = N.lib().cbn_ve_plan_outputs(h)
 
@@ -182,6 +198,9 @@ class FusedPlan:
                 self.handle = None
         except Exception:
             pass
+
+    def set_static_evidence(self, on: bool = True):
+        N.check(N.lib().cbn_ve_plan_set_static_evidence(self.handle, 1 if on else 0), self.ctx.handle)
 
     def algorithmic_bytes_per_row(self) -> int:
         ev = set()
@@ -258,7 +277,8 @@ class RowPlan:
         ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
         h = C.c_void_p()
         N.check(N.lib().cbn_ve_plan_create_rows(self.ctx.handle, len(self.evidence), ev_cards, card_t, ins, len(inputs), sts,
-                                                len(steps), N.ROWS_LOG_SPACE if log_space else 0, C.byref(h)), self.ctx.handle)
+                                                len(steps), N.ROWS_LOG_SPACE if log_space else 0, N.stream_ptr(self.device),
+                                                C.byref(h)), self.ctx.handle)
         self.handle = h
 
     def __del__(self):

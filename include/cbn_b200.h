@@ -45,7 +45,7 @@ extern "C" {
 #define CBN_API
 #endif
 
-#define CBN_ABI_VERSION 1
+#define CBN_ABI_VERSION 2
 #define CBN_MAX_FAMILY_VARS 12
 #define CBN_MAX_CARD 255
 #define CBN_UNSEEN 255
@@ -118,10 +118,11 @@ CBN_API int cbn_count_plan_create(cbn_ctx* ctx, const cbn_family* fams, int32_t 
 CBN_API void cbn_count_plan_destroy(cbn_count_plan* plan);
 CBN_API int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes, int64_t ld, int64_t n,
                   unsigned long long* counts, cbn_stream stream);
-/* the same from a HOST code matrix (pinned or pageable): chunked H2D copies overlap the counting; synchronous.
- * counts: device int64 tables as above (they accumulate). */
+/* the same from a HOST code matrix (pinned or pageable): chunked H2D copies overlap the counting on internal streams,
+ * which are ordered behind the work already queued on `stream` (the stream that last touched `counts`); synchronous:
+ * returns when the tables are complete.  counts: device int64 tables as above (they accumulate). */
 CBN_API int cbn_count_run_host(cbn_ctx* ctx, const cbn_count_plan* plan, const uint8_t* codes_host, int64_t ld, int64_t n,
-                       unsigned long long* counts);
+                       unsigned long long* counts, cbn_stream stream);
 /* introspection for the bench: number of family groups (kernel passes over the tile) */
 CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
 /* table updates per sample after merging families that share variables into super-families (<= number of families) */
@@ -197,14 +198,22 @@ typedef struct cbn_gather_table {
   int32_t has_target; /* 0: a per-row scalar (support mask) */
 } cbn_gather_table;
 
+/* Plan creation uploads descriptors (and small tables) on `stream` -- the stream the tables were produced on -- and
+ * returns after that stream has drained; from then on the plan's device data is immutable. */
 CBN_API int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                               const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
-                              cbn_ve_plan** out);
+                              cbn_stream stream, cbn_ve_plan** out);
 CBN_API void cbn_ve_plan_destroy(cbn_ve_plan* plan);
 /* Fuse several single-target plans over the SAME evidence list and target cardinality into one plan whose
  * launch reads the evidence once and writes every target's posterior (cbn_ve_run_codes_multi).  The fused
  * plan references the same table memory; the inputs can be destroyed afterwards. */
-CBN_API int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_ve_plan** out);
+CBN_API int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, int32_t n_plans, cbn_stream stream,
+                     cbn_ve_plan** out);
+/* The gather kernels are launched with programmatic dependent launch.  By default a launch waits for the previous
+ * kernel of its stream before it reads the evidence (an encode kernel may have just written it).  on = 1 declares
+ * that the evidence handed to runs of this plan is never written by the kernel preceding the run on the same stream
+ * (resident batches, CUDA-graph replay): the evidence loads then overlap the tail of the previous launch too. */
+CBN_API int cbn_ve_plan_set_static_evidence(cbn_ve_plan* plan, int32_t on);
 CBN_API int cbn_ve_plan_outputs(const cbn_ve_plan* plan);
 
 /* Per-row elimination plan: used when the evidence boundary of the target's component is too large to tabulate.
@@ -232,7 +241,7 @@ typedef struct cbn_row_step {
 } cbn_row_step;
 CBN_API int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                             const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps, int32_t n_steps,
-                            int32_t flags, cbn_ve_plan** out);
+                            int32_t flags, cbn_stream stream, cbn_ve_plan** out);
 
 /* evidence as codes: column e of the plan's evidence list at ev_codes + e * ld.
  * posterior: device float[n_rows, card_t], rows sum to 1 (all zeros when the evidence

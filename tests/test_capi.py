@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound(native):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(native.SIGNATURES) == declared, "ctypes SIGNATURES and the header disagree"
-    assert lib.cbn_abi_version() == 1
+    assert lib.cbn_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(native, tmp_path):

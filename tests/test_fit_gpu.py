@@ -247,8 +247,7 @@ def test_sample_count_lives_on_the_device_next_to_the_tables():
         assert np.array_equal(t.table_view(t.counts, name).cpu().numpy(), want)
         j, c = O.cpt_from_counts(want, 4992)
         assert np.array_equal(t.table_view(t.cond, name).cpu().numpy(), c)
-    t.counts.zero_()
-    t.n_total = 0
+    t.reset_counts()
     with pytest.raises(ValueError):
         t.finalize()
 

@@ -58,6 +58,51 @@ def test_frozen_lake_network_fit_and_infer(golden_dir):
     assert np.array_equal(pred, g["data"][:512, [0, 1, 2]][np.arange(512), 2] * 0 + g["getprob_rows"][:512].argmax(1))
 
 
+def test_wide_target_through_the_network_api(golden_dir):
+    """A target with more values than the register-resident kernels hold (obs_0: 11 values; a synthetic 16-value node):
+    ``infer``, ``infer_map`` and ``benchmarking_df`` must take the code path instead of failing."""
+    from continuousbayesiannetwork_b200 import BayesianNetwork
+
+    from oracle import cbn_oracle as O
+
+    g, df, bn = _frozen_lake(golden_dir)
+    ev = {"reward": torch.tensor(g["data"][:777, 2:3])}
+    pdf, dom = bn.infer("obs_0", ev, N_max=64)
+    assert pdf.shape == (777, 11) and dom.shape == (777, 11)
+    # P(obs | reward) by Bayes from the fitted tables
+    t = bn.tables
+    p_obs = t.table_view(t.cond, "obs_0").double().cpu().numpy()            # [11]
+    p_act = t.table_view(t.cond, "action").double().cpu().numpy()           # [4]
+    p_r = t.table_view(t.cond, "reward").double().cpu().numpy()             # [action, obs, reward]
+    joint = np.einsum("o,a,aor->or", p_obs, p_act, p_r)
+    post = joint / joint.sum(0, keepdims=True)                               # [obs, reward]
+    r_code = (g["data"][:777, 2] == t.domains[t.index["reward"]].cpu().numpy()[1]).astype(int)
+    np.testing.assert_allclose(pdf.cpu().numpy(), post[:, r_code].T, rtol=1e-5, atol=1e-12)
+    m = bn.infer_map("obs_0", ev)
+    assert np.array_equal(m.cpu().numpy(), dom[0].cpu().numpy()[post[:, r_code].argmax(0)])
+    pred = bn.benchmarking_df(df.iloc[:300], "obs_0", batch_size=128)
+    assert pred.shape == (300,) and set(np.unique(pred)) <= set(g["domain_obs_0"].tolist())
+    # 16-value target, 2 evidence parents, synthetic
+    rng = np.random.default_rng(5)
+    n = 50_000
+    a = rng.integers(0, 3, n)
+    b = rng.integers(0, 2, n)
+    x = (a * 5 + b * 3 + rng.integers(0, 6, n)) % 16
+    frame = pd.DataFrame({"a": a.astype(np.float32), "b": b.astype(np.float32), "x": x.astype(np.float32)})
+    dag = nx.DiGraph()
+    dag.add_edges_from([("a", "x"), ("b", "x")])
+    bn2 = BayesianNetwork(dag, frame, PL, INF, device=DEV)
+    ev = {"a": torch.tensor(frame["a"].values[:999]).reshape(-1, 1), "b": torch.tensor(frame["b"].values[:999]).reshape(-1, 1)}
+    pdf, dom = bn2.infer("x", ev, N_max=16)
+    assert pdf.shape == (999, 16)
+    mle = O.fit_mle(torch.tensor(frame["x"].values), torch.tensor(np.stack([frame["a"].values, frame["b"].values])))
+    want = O.get_prob(mle, dom.cpu(), torch.stack([ev["a"], ev["b"]], dim=1))
+    want = want / want.sum(1, keepdim=True)
+    np.testing.assert_allclose(pdf.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-12)
+    pred = bn2.benchmarking_df(frame.iloc[:500], "x", batch_size=256)
+    assert np.array_equal(pred, dom[0].cpu().numpy()[want[:500].argmax(1).numpy()].astype(np.float64))
+
+
 def test_true_posterior_where_the_reference_is_not_one(golden_dir):
     """Only `action` observed: the reference averages P(r|obs,a) uniformly over obs; the
     engine returns the actual posterior sum_obs P(obs) P(r|obs,a)."""

@@ -89,6 +89,75 @@ def test_alarm_and_random_dags():
         _check(spec, infer, spec.names[vs[0]], [spec.names[v] for v in vs[1:]], codes[vs[1:]].T)
 
 
+def _all_configurations(cards):
+    """Every configuration of variables with cardinalities ``cards``, row-major (last fastest): int64 [prod, len]."""
+    grids = np.indices(cards).reshape(len(cards), -1)
+    return np.ascontiguousarray(grids.T)
+
+
+def _oracle_chunked(net, target, ids, ev, dtype, chunk=1 << 16):
+    return np.concatenate([O.ve_posterior(net, target, ids, ev[s: s + chunk], dtype=dtype) for s in range(0, ev.shape[0], chunk)])
+
+
+def test_alarm_compiled_tables_over_every_evidence_configuration():
+    """BASELINE.json configs[2]: the compiled table IS the answer of every row, so it is checked whole -- all 839,808
+    configurations of the 12 evidence variables, for the four targets, single plans and the fused (interleaved) launch,
+    against the fp64 textbook-VE oracle; plus Asia's 16 configurations against fp64 enumeration."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts
+
+    spec = synth.alarm()
+    _, infer = install_cpts(spec, DEV)
+    net = _net(spec)
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    ev = _all_configurations([spec.cards[i] for i in ids])
+    assert ev.shape[0] == 839808
+    dev_ev = _codes_matrix(ev)
+    fused = infer.fused_plan(synth.ALARM_TARGETS, synth.ALARM_EVIDENCE).run_codes(dev_ev, ev.shape[0])
+    worst = 0.0
+    for tg, fo in zip(synth.ALARM_TARGETS, fused):
+        got = infer.plan(tg, synth.ALARM_EVIDENCE).run_codes(dev_ev, ev.shape[0])
+        assert torch.equal(got, fo)
+        want = _oracle_chunked(net, spec.names.index(tg), ids, ev, torch.float64)
+        got = got.cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(want, 1e-30))))
+    assert worst < RTOL
+    spec = synth.asia()
+    _, infer = install_cpts(spec, DEV)
+    names = ["asia", "smoke", "xray", "dysp"]
+    ev = _all_configurations([2, 2, 2, 2])
+    for tg in ("lung", "tub", "bronc"):
+        got = infer.plan(tg, names).run_codes(_codes_matrix(ev), 16).cpu().numpy()
+        truth = O.enumerate_posterior(_net(spec), spec.names.index(tg), [spec.names.index(e) for e in names], ev)
+        np.testing.assert_allclose(got, truth, rtol=RTOL, atol=1e-30)
+
+
+def test_config4_ktree200_tables_on_a_stratified_sample():
+    """BASELINE.json configs[3], query half: the 8 bench patterns (4^10 = 1,048,576 evidence configurations each) on
+    32,768 configurations drawn UNIFORMLY from the configuration space -- not from the joint, so rare configurations are
+    covered like common ones -- against the fp64 oracle (the CPU oracle eliminates ~190 hidden variables per row:
+    ~15,000 rows/s, which bounds the sample), under the default planner and under an L2-sized merge budget."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import bind_inference, install_cpts
+
+    spec = synth.random_ktree_dag()
+    tables, infer = install_cpts(spec, DEV)
+    small = bind_inference(tables, merge_budget_cells=1 << 16)
+    net = _net(spec)
+    rng = np.random.default_rng(1240)
+    cfg = np.random.default_rng(99)
+    n = 1 << 15
+    for _ in range(8):
+        vs = [int(v) for v in rng.choice(spec.n, size=11, replace=False)]
+        ev = cfg.integers(0, 4, size=(n, 10))
+        names = [spec.names[v] for v in vs[1:]]
+        want = _oracle_chunked(net, vs[0], vs[1:], ev, torch.float64, chunk=4096)
+        for eng in (infer, small):
+            got = eng.plan(spec.names[vs[0]], names).run_codes(_codes_matrix(ev), n).cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+
+
 def test_config4_ktree200_patterns():
     """BASELINE.json configs[3], query half: 200-node card-4 partial 8-tree, random target + 10 random evidence
     variables (the 8 patterns bench.py times), against the fp32 and fp64 oracle."""
