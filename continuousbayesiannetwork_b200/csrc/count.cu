@@ -3,20 +3,27 @@
 // (reference cbn/parameter_learning/brute_force.py:17-53) and the Python loop over nodes of
 // BayesianNetwork._train (cbn/base/bayesian_network.py:138-160).
 //
-// Kernel structure (count_tiles_kernel):
-//   * families are clustered into groups by column overlap; one CTA owns one group's tables as
-//     privatised uint32 counters in shared memory (flushed once, at the end, with 64-bit atomics);
-//   * the CTA walks tiles of 2048 samples: the group's columns of the tile are staged in shared
-//     memory by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
-//     double-buffered so the copy of tile k+1 overlaps the histogram of tile k;
-//   * every thread owns 8 consecutive samples (one 64-bit word per column) and walks the group's flat
-//     (variable, family) entry stream, computing the family indices with SIMD-within-a-register
-//     arithmetic: trailing variables whose partial index fits a byte are multiplied in 4x8-bit lanes,
-//     the others in 2x16-bit lanes;
-//   * updates are branch-free shared-memory atomic increments (ATOMS.POPC.INC); an out-of-range index is
-//     clamped onto a spare cell per family that is never flushed.
-// count_direct_kernel is the same arithmetic straight from global memory: used for the tail
-// (n % 2048 samples) and, with global atomics, for families too large for shared memory.
+// Plan (host, once per network):
+//   * families that share variables are merged into super-families -- the union scope of several families, at most 256
+//     cells -- so ONE shared-memory update per sample serves all member families; the member tables are integer
+//     marginals of the super table, produced when the CTA flushes;
+//   * tables are clustered into groups by column overlap; one CTA owns one group's tables as privatised uint32 counters
+//     in shared memory (flushed once, at the end, with 64-bit atomics, so calls accumulate).
+// Kernel (count_tiles_kernel): the CTA walks tiles of 1024-8192 samples.  The group's columns of a tile are staged in
+// shared memory by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx), 2-4 stages deep; every warp
+// issues the copies of its share of the columns (one warp can only start a 1 KB copy every ~75 clocks,
+// tools/probe_bulk.cu).  Work is table-stationary: per tile a warp takes one (table, whole tile) unit -- or a part of the
+// tile when the group has fewer tables than warps -- keeps the table's column offsets and strides in registers (variable
+// counts are template parameters, dispatched once per unit) and walks the tile 8 samples per lane and iteration: one
+// 64-bit shared-memory load per column, index arithmetic SIMD-within-a-register (variables whose partial index stays
+// below 256 in 4 x 8-bit lanes, the rest in 2 x 16-bit lanes), branch-free shared-memory reductions (red.shared.add,
+// SASS ATOMS.POPC.INC); an out-of-range index is clamped onto a spare cell per table that is never flushed.  A word with
+// a code >= 128 (cardinality > 128 or CBN_UNSEEN) takes an exact scalar path.
+// What bounds it (tools/probe_atoms.cu, tools/probe_lanepriv.cu): the shared-memory pipe.  An
+// ATOMS over 32 random cells costs ~3.5 wavefronts (bank conflicts between different addresses; same-address lanes are
+// merged for free), a 64-bit tile read 2, and the pipe retires one wavefront per clock and SM.
+// count_direct_kernel is the same arithmetic straight from global memory: used for the tail (n % tile samples) and, with
+// global atomics, for families too large for shared memory.
 #include <stdlib.h>
 #include <string.h>
 
@@ -241,16 +248,18 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) count_tiles_kernel(
   const int lane = threadIdx.x & 31;
   const int64_t my_tiles = x < n_tiles ? (n_tiles - x + xstride - 1) / xstride : 0;
 
-  auto issue = [&](int i, int b) {   // warp 0: this CTA's i-th tile into stage b (== i % n_stages)
+  // every warp issues the bulk copies of its share of the columns (one warp can only start a 1 KB copy every ~75 clocks:
+  // tools/probe_bulk.cu); thread 0 posts the expected byte count
+  constexpr int N_WARPS_ISSUE = TPB / 32;
+  auto issue = [&](int i, int b) {   // this CTA's i-th tile into stage b (== i % n_stages)
     const int64_t tile = x + i * xstride;
-    if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
-    __syncwarp();
-    if (lane < G.n_cols)
-      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(lane) * tile_samples, codes + int64_t(s_cols[lane]) * ld + tile * tile_samples,
+    if (threadIdx.x == 0) mbar_expect_tx(&full[b], tile_bytes);
+    const int c = (threadIdx.x >> 5) + lane * N_WARPS_ISSUE;
+    if (c < G.n_cols)
+      bulk_g2s(stage + size_t(b) * tile_bytes + size_t(c) * tile_samples, codes + int64_t(s_cols[c]) * ld + tile * tile_samples,
                (uint32_t)tile_samples, &full[b]);
   };
-  if (threadIdx.x < 32)
-    for (int i = 0; i < my_tiles && i < n_stages - 1; ++i) issue(i, i);
+  for (int i = 0; i < my_tiles && i < n_stages - 1; ++i) issue(i, i);
 
   const int n_fams = G.n_fams;
   // few families: split every family's tile into 2, 4 or 8 parts so the 8 warps stay balanced
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) count_tiles_kernel(
   const int n_my = (int)my_tiles;
   for (int i = 0; i < n_my; ++i) {
     // the stage tile i-1 used was released by the __syncthreads that closed the previous iteration
-    if (threadIdx.x < 32 && i + n_stages - 1 < n_my) issue(i + n_stages - 1, b_fill);
+    if (i + n_stages - 1 < n_my) issue(i + n_stages - 1, b_fill);
     mbar_wait(&full[b], phase);
     const unsigned char* tile = stage + size_t(b) * tile_bytes;
     // family-stationary: a warp takes (family, part of the tile) units, so the per-family metadata is loop invariant;
@@ -759,12 +768,13 @@ extern "C" int cbn_count_run(cbn_ctx* ctx, const cbn_count_plan* plan, const uin
   if (ld < n || (ld % 16) != 0 || !is_aligned(codes, 16))
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_count_run: code matrix needs ld >= n, ld %% 16 == 0 and a 16-byte aligned base (ld=%lld, n=%lld)",
                     (long long)ld, (long long)n);
-  if (n == 0) return CBN_OK;
   DeviceGuard g(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t chunk = int64_t(1) << 33;  // private uint32 counters cannot overflow below this (>= 64 CTAs per group)
+  // a CTA's private uint32 counters see at most the samples of one launch: 2^31 per launch cannot overflow them however
+  // few CTAs a group gets (a multiple of every tile size, so alignment is preserved)
+  const int64_t chunk = int64_t(1) << 31;
   for (int64_t start = 0; start < n; start += chunk) {
-    const int64_t m = std::min(chunk, n - start);  // start is a multiple of 2^33: alignment is preserved
+    const int64_t m = std::min(chunk, n - start);
     const uint8_t* base = codes + start;
     const int64_t n_tiles = m / plan->tile_samples;
     const int64_t tail = m - n_tiles * plan->tile_samples;
