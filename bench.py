@@ -334,8 +334,20 @@ class Env:
         e1.record()
         torch.cuda.synchronize()
         est = self.max_over_ranks(e0.elapsed_time(e1) / 1e3 / 10)
-        p = max(1, math.ceil(min_region_s / (steps * est)))
-        p = min(p, 2048)
+        if est < 50e-6:
+            # launch-latency scale: eager launches overestimate the pass; time a small graph of passes instead
+            n = max(ring, 8) * 4
+            g = self.graph_of([(lambda j=j: one_pass(j)) for j in range(n)])
+            g.replay()
+            self.barrier()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            est = min(est, self.max_over_ranks(e0.elapsed_time(e1) / 1e3 / n))
+            del g
+        p = max(1, math.ceil(1.15 * min_region_s / (steps * est)))
+        p = min(p, 4096)
         return (p + ring - 1) // ring * ring, est
 
 

@@ -86,6 +86,7 @@ class RowStep(C.Structure):
 
 
 ROWS_LOG_SPACE = 1
+COMM_ID_BYTES = 128
 
 # name -> (restype, argtypes); also the list the CPU test checks against the header
 _P = C.c_void_p
@@ -105,6 +106,11 @@ SIGNATURES = {
     "cbn_count_run_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "cbn_count_plan_groups": (C.c_int, [_P]),
     "cbn_count_plan_updates_per_sample": (C.c_int, [_P]),
+    "cbn_comm_unique_id": (C.c_int, [_P]),
+    "cbn_comm_create": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "cbn_comm_destroy": (None, [_P]),
+    "cbn_comm_size": (C.c_int, [_P]),
+    "cbn_counts_allreduce": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "cbn_cpt_from_counts": (C.c_int, [_P, _P, C.POINTER(Family), C.c_int32, C.c_longlong, _P, _P, _P]),
     "cbn_cpt_from_plan": (C.c_int, [_P, _P, _P, C.c_longlong, _P, _P, _P]),
     "cbn_cpt_from_plan_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

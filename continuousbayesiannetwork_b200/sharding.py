@@ -33,11 +33,62 @@ def shard_range(n: int, rank: int, world_size: int, align: int = 16) -> Tuple[in
     return s, max(s, e)
 
 
+_library_comms = {}     # device index -> cbn_comm handle (the library's own NCCL communicator)
+
+
+def library_comm(device):
+    """The library's communicator for ``device`` (``cbn_comm_create``), bootstrapped through the torch.distributed group:
+    only the 128-byte NCCL id travels through torch; the collective itself is the C ABI's ``cbn_counts_allreduce``.
+    Returns None when NCCL cannot be bound (``CBN_LIBRARY_COMM=0`` also disables it): callers then use torch.distributed."""
+    import ctypes as C
+    import os
+
+    from . import _native as N
+
+    if os.environ.get("CBN_LIBRARY_COMM", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+        return None
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return None
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _library_comms:
+        return _library_comms[idx]
+    rank, world_size = dist.get_rank(), dist.get_world_size()
+    ident = torch.zeros(N.COMM_ID_BYTES + 1, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_uint8 * N.COMM_ID_BYTES)()
+        ok = N.lib().cbn_comm_unique_id(buf) == N.OK
+        ident[: N.COMM_ID_BYTES] = torch.tensor(list(buf), dtype=torch.uint8)
+        ident[N.COMM_ID_BYTES] = 1 if ok else 0
+    on_dev = dist.get_backend() == "nccl"
+    t = ident.to(dev) if on_dev else ident
+    dist.broadcast(t, 0)
+    ident = t.cpu()
+    handle = None
+    if int(ident[N.COMM_ID_BYTES]) == 1:
+        ctx = N.context_for(dev)
+        raw = (C.c_uint8 * N.COMM_ID_BYTES)(*ident[: N.COMM_ID_BYTES].tolist())
+        h = C.c_void_p()
+        N.check(N.lib().cbn_comm_create(ctx.handle, raw, world_size, rank, C.byref(h)), ctx.handle)
+        handle = (ctx, h)
+    _library_comms[idx] = handle
+    return handle
+
+
 def allreduce_counts(counts: torch.Tensor) -> torch.Tensor:
-    """In-place sum of the int64 count tables over all ranks (a no-op in a single process)."""
+    """In-place sum of the int64 count tables over all ranks (a no-op in a single process).  Device tables go through
+    the library's own collective (``cbn_counts_allreduce`` = ncclAllReduce(int64, sum) on the current stream); host
+    tensors (the gloo CPU tests) and processes without NCCL through torch.distributed."""
     assert counts.dtype == torch.int64
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        comm = library_comm(counts.device) if counts.is_cuda else None
+        if comm is not None and counts.is_contiguous():
+            from . import _native as N
+
+            ctx, h = comm
+            N.check(N.lib().cbn_counts_allreduce(ctx.handle, h, counts.data_ptr(), counts.numel(), N.stream_ptr(counts.device)), ctx.handle)
+        else:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts
 
 

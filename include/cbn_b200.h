@@ -128,6 +128,22 @@ CBN_API int cbn_count_plan_groups(const cbn_count_plan* plan);
 /* table updates per sample after merging families that share variables into super-families (<= number of families) */
 CBN_API int cbn_count_plan_updates_per_sample(const cbn_count_plan* plan);
 
+/* ---- multi-GPU: the one collective of the path ------------------------------------------
+ * A sharded fit (contiguous sample ranges per GPU, one process per GPU) counts into full private tables and sums them
+ * once: cbn_counts_allreduce is an in-place ncclAllReduce(ncclInt64, ncclSum) over NVLink / NVSwitch on `stream`
+ * (the reference has no distributed code; this sits between brute_force.py:42 "counts" and :43 "counts / counts.sum()").
+ * Integer addition is associative, so the tables are bit-identical on every rank and for any number of ranks.
+ * NCCL is bound at run time (dlopen of libnccl.so.2); without it these entry points return CBN_ERR_UNSUPPORTED.
+ * Bootstrap: rank 0 calls cbn_comm_unique_id, the caller ships the 128 bytes to every rank by any means (MPI, a file,
+ * torch.distributed), then every rank calls cbn_comm_create (collective). */
+#define CBN_COMM_ID_BYTES 128
+typedef struct cbn_comm cbn_comm;
+CBN_API int cbn_comm_unique_id(uint8_t* id_out /* [CBN_COMM_ID_BYTES] */);
+CBN_API int cbn_comm_create(cbn_ctx* ctx, const uint8_t* id, int32_t n_ranks, int32_t rank, cbn_comm** out);
+CBN_API void cbn_comm_destroy(cbn_comm* comm);
+CBN_API int cbn_comm_size(const cbn_comm* comm);
+CBN_API int cbn_counts_allreduce(cbn_ctx* ctx, cbn_comm* comm, long long* counts, int64_t n_cells, cbn_stream stream);
+
 /* ---- tables -> probabilities --------------------------------------------------------
  * joint[cell] = fp32(count) / fp32(n_total)                     (brute_force.py:43)
  * cond[pa, x] = joint[pa, x] / (sum_x' joint[pa, x'] + 1e-10)   (brute_force.py:228-241)

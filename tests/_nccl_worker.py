@@ -22,6 +22,18 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
+    # the library's own collective (cbn_counts_allreduce) against torch.distributed's on the same buffer
+    from continuousbayesiannetwork_b200 import _native as N
+
+    comm = sharding.library_comm(dev)
+    assert comm is not None, "cbn_comm could not be created (NCCL not loadable?)"
+    assert N.lib().cbn_comm_size(comm[1]) == world
+    g = torch.Generator(device=dev); g.manual_seed(100 + rank)
+    a = torch.randint(0, 1 << 40, (100_003,), dtype=torch.int64, device=dev, generator=g)
+    b = a.clone()
+    sharding.allreduce_counts(a)                       # library path
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)           # torch path
+    assert torch.equal(a, b), "cbn_counts_allreduce differs from torch.distributed.all_reduce"
     for spec, n1, n2 in ((synth.alarm(), 3_000_017, 1_000_003), (synth.random_ktree_dag(), 400_009, 65_537)):
         t = tables_from_spec(spec, dev)
         s1, e1 = sharding.shard_range(n1, rank, world)
