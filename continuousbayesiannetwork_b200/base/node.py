@@ -1,6 +1,5 @@
 """Node / factor builder -- the reference's ``Node`` surface (cbn/base/node.py:17-381,
 plotting excluded) on the B200 tables."""
-import random
 from typing import Dict, List, Tuple
 
 import torch
@@ -133,27 +132,42 @@ class Node:
         return None, None
 
     def sample_domain(self, node: str, N: int = 1024) -> torch.Tensor:
-        """N evaluation points of a variable (reference node.py:286-333): rounded-linspace subsample if
-        N < card, the domain itself if N == card, the domain padded with random unseen values if N > card."""
-        min_value, max_value, _, domain_values = self.info[node]
-        cardinality = domain_values.shape[0]
-        if N < cardinality:
-            indices = torch.linspace(start=0, end=cardinality - 1, steps=N).round().long()
-            return domain_values[indices.to(domain_values.device)]
-        if N == cardinality:
-            return domain_values
-        needed = N - cardinality
-        existing = set(domain_values.tolist())
-        lo, hi = float(min_value), float(max_value)
-        new_values = []
-        while len(new_values) < needed:
-            candidate = random.uniform(lo, hi) if hi > lo else lo + 1.0 + len(new_values)
-            if candidate not in existing:
-                new_values.append(candidate)
-                existing.add(candidate)
-        extra = torch.tensor(new_values, dtype=domain_values.dtype, device=domain_values.device)
-        out, _ = torch.sort(torch.cat([domain_values, extra]))
-        return out
+        """N evaluation points of a variable, sorted.  Same contract as the reference's helper (node.py:286-333): a
+        rounded-linspace subsample of the fitted domain when N is smaller than it, the domain itself when equal, and the
+        domain plus N - card extra points inside [min, max] otherwise.  The extra points are never-observed values (every
+        lookup on them is zero, so they do not change any posterior); the reference draws them at random, here they are
+        placed deterministically by bisecting the currently widest gap of the domain, so grids are reproducible."""
+        lo, hi, _, dom = self.info[node]
+        card = int(dom.shape[0])
+        if N <= card:
+            if N == card:
+                return dom
+            pick = torch.linspace(0, card - 1, N).round().long().to(dom.device)
+            return dom[pick]
+        import heapq
+
+        pts = [float(v) for v in dom.tolist()]
+        if card == 1 or float(hi) <= float(lo):
+            # a single observed value leaves no gap to split: continue above it in unit steps
+            pts += [pts[-1] + 1.0 + k for k in range(N - card)]
+            return torch.tensor(pts, dtype=dom.dtype, device=dom.device)
+        gaps = [(-(b - a), a, b) for a, b in zip(pts, pts[1:])]
+        heapq.heapify(gaps)
+        have = set(pts)
+        while len(pts) < N:
+            _, a, b = heapq.heappop(gaps)
+            mid = float(torch.tensor(0.5 * (a + b), dtype=dom.dtype))       # round to the column's dtype before comparing
+            if mid in have or not (a < mid < b):
+                continue                                                    # gap too narrow for this dtype: drop it
+            have.add(mid)
+            pts.append(mid)
+            heapq.heappush(gaps, (-(mid - a), a, mid))
+            heapq.heappush(gaps, (-(b - mid), mid, b))
+            if not gaps:
+                break
+        while len(pts) < N:                                                 # every gap exhausted (pathological domains)
+            pts.append(max(pts) + 1.0)
+        return torch.tensor(sorted(pts), dtype=dom.dtype, device=dom.device)
 
     def _batched_meshgrid_combinations(self, input_tensor: torch.Tensor) -> torch.Tensor:
         """[n_queries, n_parents, N] -> [n_queries, n_parents, N^n_parents], 'ij' order (reference

@@ -68,7 +68,53 @@ __global__ void __launch_bounds__(256) normalize_last_kernel(float* x, long long
     for (int t = 0; t < card; ++t) p[t] *= inv;
   }
 }
+// every slice (n_slices contiguous runs of slice_size cells) is divided by its maximum; all-zero slices stay zero.
+// One warp per slice, lanes strided over the cells.
+__global__ void __launch_bounds__(256) rescale_slices_kernel(float* __restrict__ x, long long n_slices, int slice_size) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long sl = warp0; sl < n_slices; sl += n_warps) {
+    float* p = x + sl * slice_size;
+    float m = 0.0f;
+    for (int i = lane; i < slice_size; i += 32) m = fmaxf(m, p[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (m > 0.0f && m != 1.0f) {
+      const float inv = 1.0f / m;
+      for (int i = lane; i < slice_size; i += 32) p[i] *= inv;
+    }
+  }
+}
+// slices of at most 8 cells: one thread per slice
+__global__ void __launch_bounds__(256) rescale_small_slices_kernel(float* __restrict__ x, long long n_slices, int slice_size) {
+  for (long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x; sl < n_slices; sl += (long long)gridDim.x * blockDim.x) {
+    float* p = x + sl * slice_size;
+    float m = 0.0f;
+    for (int i = 0; i < slice_size; ++i) m = fmaxf(m, p[i]);
+    if (m > 0.0f && m != 1.0f) {
+      const float inv = 1.0f / m;
+      for (int i = 0; i < slice_size; ++i) p[i] *= inv;
+    }
+  }
+}
 }  // namespace
+
+extern "C" int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, cbn_stream stream) {
+  if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_factor_rescale: ctx is NULL");
+  if (!table || n_slices < 0 || slice_size < 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_factor_rescale: bad argument");
+  if (n_slices == 0) return CBN_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (slice_size <= 8) {
+    const int blocks = (int)std::min<long long>((n_slices + 255) / 256, (long long)ctx->sm_count * 16);
+    rescale_small_slices_kernel<<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+  } else {
+    const int blocks = (int)std::min<long long>((n_slices + 7) / 8, (long long)ctx->sm_count * 16);
+    rescale_slices_kernel<<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+  }
+  CBN_CHECK_LAUNCH(ctx);
+  return CBN_OK;
+}
 
 extern "C" int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_factor_contract: ctx is NULL");
@@ -366,7 +412,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
   float p[4][CT];
   uint32_t bad = 0, ibad = 0;
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-  int cur = -1;
+  int cur = -1, n_mul = 0;
   for (int k = 0; k < n_tables; ++k) {
     const GTable& T = st[k];
     const int flags = T.flags;
@@ -374,6 +420,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       if (cur >= 0) finish_any4<CT>(p, bad, (outs.normalize_mask >> cur) & 1u, quad, n_rows, outs, cur, st_pol);
       cur = T.out_id;
       bad = 0;
+      n_mul = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -435,6 +482,19 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
         load_slice<CT>(base + idx[r], v);
 #pragma unroll
         for (int t = 0; t < CT; ++t) p[r][t] *= v[t];
+      }
+      // range control: every table slice is scaled to maximum 1 at compile time; a long product of such slices is
+      // pulled back to maximum 1 every fourth factor (a per-row constant, it cancels in the normalisation)
+      if ((++n_mul & 3) == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float m = p[r][0];
+#pragma unroll
+          for (int t = 1; t < CT; ++t) m = fmaxf(m, p[r][t]);
+          const float inv = m > 0.0f ? __frcp_rn(m) : 1.0f;
+#pragma unroll
+          for (int t = 0; t < CT; ++t) p[r][t] *= inv;
+        }
       }
     } else {
 #pragma unroll
@@ -1223,7 +1283,7 @@ __device__ __noinline__ float row_step_generic(const RowStepDev& S, const int* _
 }
 
 template <bool LOG>
-__global__ void __launch_bounds__(ROWS_TPB) ve_rows_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
+__global__ void __launch_bounds__(ROWS_TPB, 4) ve_rows_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
                                                            const RowStepDev* __restrict__ steps, int n_steps, int temp_floats,
                                                            const int* __restrict__ off_pool, int off_ints, int n_evidence,
                                                            const uint8_t* __restrict__ ev, int64_t ld, int64_t n_rows,

@@ -24,8 +24,9 @@ class ExactInference(BaseInference):
             raise ValueError(f"normalization must be 'row' or 'global_max', got {self.normalization!r}")
         self._budget = {k: int(config[k]) for k in ("table_budget_cells", "merge_budget_cells", "row_temp_floats")
                         if config and k in config}
-        if config and "log_space" in config:
-            self._budget["log_space"] = bool(config["log_space"])
+        for k in ("log_space", "rescale"):
+            if config and k in config:
+                self._budget[k] = bool(config[k])
 
     def bind(self, tables):
         """Attach the fitted network tables (called by BayesianNetwork after every fit)."""

@@ -36,6 +36,25 @@ def shard_range(n: int, rank: int, world_size: int, align: int = 16) -> Tuple[in
 _library_comms = {}     # device index -> cbn_comm handle (the library's own NCCL communicator)
 
 
+class _StdoutToStderr:
+    """NCCL may print its version banner on stdout when it is first initialised in a process; a caller that prints
+    machine-readable output there (bench.py's JSON line) must not see it."""
+
+    def __enter__(self):
+        import os
+        import sys
+
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        import os
+
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def library_comm(device):
     """The library's communicator for ``device`` (``cbn_comm_create``), bootstrapped through the torch.distributed group:
     only the 128-byte NCCL id travels through torch; the collective itself is the C ABI's ``cbn_counts_allreduce``.
@@ -57,7 +76,8 @@ def library_comm(device):
     ident = torch.zeros(N.COMM_ID_BYTES + 1, dtype=torch.uint8)
     if rank == 0:
         buf = (C.c_uint8 * N.COMM_ID_BYTES)()
-        ok = N.lib().cbn_comm_unique_id(buf) == N.OK
+        with _StdoutToStderr():
+            ok = N.lib().cbn_comm_unique_id(buf) == N.OK
         ident[: N.COMM_ID_BYTES] = torch.tensor(list(buf), dtype=torch.uint8)
         ident[N.COMM_ID_BYTES] = 1 if ok else 0
     on_dev = dist.get_backend() == "nccl"
@@ -69,7 +89,9 @@ def library_comm(device):
         ctx = N.context_for(dev)
         raw = (C.c_uint8 * N.COMM_ID_BYTES)(*ident[: N.COMM_ID_BYTES].tolist())
         h = C.c_void_p()
-        N.check(N.lib().cbn_comm_create(ctx.handle, raw, world_size, rank, C.byref(h)), ctx.handle)
+        with _StdoutToStderr():
+            rc = N.lib().cbn_comm_create(ctx.handle, raw, world_size, rank, C.byref(h))
+        N.check(rc, ctx.handle)
         handle = (ctx, h)
     _library_comms[idx] = handle
     return handle

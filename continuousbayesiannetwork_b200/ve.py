@@ -35,6 +35,13 @@ class PlanTooLarge(NotImplementedError):
     pass
 
 
+def _prod(it) -> int:
+    p = 1
+    for x in it:
+        p *= int(x)
+    return p
+
+
 @dataclass
 class Factor:
     scope: List[int]                     # variable ids; tensor is row-major over this list
@@ -58,6 +65,8 @@ class PlanStats:
     support_unchecked: bool = False
     per_row_hidden: int = 0                      # hidden variables left to the per-row executor (0 = gather plan)
     per_row_madds: int = 0                       # multiply-adds of the per-row schedule, per evidence row
+    per_row_slice_cells: int = 0                 # cells of the static tables' slices one evidence row reads (per-row plans)
+    contraction_gpu_ms: float = 0.0              # device time of the compile-time contraction kernels (CUDA events)
     relevant_evidence: List[int] = field(default_factory=list)
 
 
@@ -378,8 +387,14 @@ class VECompiler:
     """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
 
     def __init__(self, tables, table_budget_cells: int = 1 << 28, merge_budget_cells: int = 1 << 24,
-                 check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False):
+                 check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False, rescale: bool = True):
         self.t = tables
+        # range control of the compile-time elimination: after every contraction each evidence slice of the result is
+        # divided by its maximum (cbn_factor_rescale) -- a factor of the evidence configuration only, which cancels in the
+        # final normalisation -- so products of many small likelihoods stay inside the fp32 range
+        self.rescale = bool(rescale)
+        self._ev_set: set = set()
+        self._events: list = []
         self.table_budget = int(table_budget_cells)
         self.merge_budget = int(merge_budget_cells)
         self.check_support = check_support
@@ -441,7 +456,23 @@ class VECompiler:
         out = torch.empty(max(n_out, 1), dtype=torch.float32, device=self.t.device)
         d.out = out.data_ptr()
         d.normalize_last = 1 if normalize_last else 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         N.check(N.lib().cbn_factor_contract(self.t.ctx.handle, C.byref(d), N.stream_ptr(self.t.device)), self.t.ctx.handle)
+        if self.rescale and not normalize_last:
+            # evidence axes are the slowest axes of every factor (sort_scope): one contiguous slice per evidence configuration
+            lead = 0
+            while lead < len(out_scope) and out_scope[lead] in self._ev_set:
+                lead += 1
+            n_slices = 1
+            for v in out_scope[:lead]:
+                n_slices *= cards[v]
+            slice_size = max(n_out, 1) // max(n_slices, 1)
+            if all(v not in self._ev_set for v in out_scope[lead:]):
+                N.check(N.lib().cbn_factor_rescale(self.t.ctx.handle, out.data_ptr(), n_slices, slice_size,
+                                                   N.stream_ptr(self.t.device)), self.t.ctx.handle)
+        e1.record()
+        self._events.append((e0, e1))
         return Factor(out_scope, out)
 
     # ---------------------------------------------------------------- compile
@@ -466,6 +497,9 @@ class VECompiler:
             # structure-only pass first: a query that does not fit fails here, before any table is contracted
             self.compile(target, evidence, do=do, dry=True)
         Eset = set(E)
+        self._ev_set = Eset
+        if not dry:
+            self._events = []
         order_key = {v: i for i, v in enumerate(E)}
         stats = PlanStats()
 
@@ -545,9 +579,11 @@ class VECompiler:
             stats.final_tables = [(tuple(f.scope), f.size(cards)) for f in finals]
             if self.log_space and not dry:
                 finals = [Factor(f.scope, torch.log(f.tensor)) for f in finals]
+            stats.per_row_slice_cells = sum(int(f.size(cards) // max(1, _prod(cards[v] for v in f.scope if v in Eset))) for f in finals)
             plan = self._row_plan(T, E, finals, left, stats, dry)
             if dry:
                 return stats
+            stats.contraction_gpu_ms = self._drain_events()
             self._cache[key] = plan
             return plan
         finals = self._merge_finals(finals, sort_scope, stats, dry, T)
@@ -563,9 +599,18 @@ class VECompiler:
         if not with_t:
             # target independent of everything kept (cannot happen: P(T|pa) always mentions T)
             raise RuntimeError("internal: no final factor mentions the target")
+        stats.contraction_gpu_ms = self._drain_events()
         plan = QueryPlan(t, T, E, cards[T], finals, normalize, stats)
         self._cache[key] = plan
         return plan
+
+    def _drain_events(self) -> float:
+        if not self._events:
+            return 0.0
+        self._events[-1][1].synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        self._events = []
+        return ms
 
     def _eliminate(self, factors: List[Factor], hidden: List[int], sort_scope, stats: PlanStats, dry: bool, T: int,
                    partial: bool = False):

@@ -199,6 +199,12 @@ typedef struct cbn_contract {
   int32_t normalize_last; /* 1: divide every slice over the LAST out dim by its sum (0 if the sum is 0) */
 } cbn_contract;
 CBN_API int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stream stream);
+/* Range control of the compile-time elimination (the linear-space counterpart of working in log space): `table` holds
+ * n_slices contiguous slices of slice_size cells -- one slice per configuration of the factor's evidence axes, which are
+ * its slowest axes -- and every slice is divided by its own maximum (all-zero slices stay zero).  A factor that depends on
+ * evidence axes only cancels in the final normalisation over the target, so posteriors are unchanged while products of
+ * many small likelihoods stay inside the fp32 range. */
+CBN_API int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, cbn_stream stream);
 
 /* A compiled query: after the hidden variables have been eliminated once with the
  * evidence variables kept as free axes, every row only gathers
