@@ -750,6 +750,10 @@ def bench_ktree200(env, args):
                  "plan_compile_ms_total": compile_ms, "queries_per_s_incl_compile_one_pass": rows * len(pats) * world / (compile_ms / 1e3 + sec / (k * P)),
                  "table_cells": [[c for _, c in p.stats.final_tables] for p, _, _, _ in pats],
                  "contraction_madds": [p.stats.contraction_madds for p, _, _, _ in pats],
+                 "contraction_gpu_ms": [round(p.stats.contraction_gpu_ms, 3) for p, _, _, _ in pats],
+                 "contraction_note": "every elimination step contracts ONE variable (sum over its <= 4 values here): arithmetic intensity is "
+                                     "sum_card x n_inputs multiply-adds per output cell written, so the steps are bound by writing their output tables, "
+                                     "not by arithmetic -- no step is a dense GEMM-shaped contraction that tensor cores could speed up",
                  "roofline": roofline(env, alg, sec / (k * P), "gather_codes_kernel<4> x 8 patterns",
                                       extra={"launch_note": "one 'launch' = the 8 pattern launches of a pass"})}
     out["_keep"] = (spec, t, infer, pats)
@@ -804,6 +808,7 @@ def bench_layered(env, args):
     row_pats = [x for x in pats if isinstance(x[0], RowPlan)]
     gat_pats = [x for x in pats if not isinstance(x[0], RowPlan)]
     row_madds = sum(p.stats.per_row_madds for p, _, _ in row_pats)
+    row_slice_bytes = sum(4 * p.stats.per_row_slice_cells + len(p.stats.relevant_evidence) + 4 * p.card_t for p, _, _ in row_pats)
 
     def run(ps):
         def f(_i=0):
@@ -825,7 +830,13 @@ def bench_layered(env, args):
             "per_row_plans": {"plans": len(row_pats), "multiply_adds_per_row_all_plans": row_madds, "ms_per_pass": row_sec * 1e3,
                               "queries_per_s": rows * world * len(row_pats) / row_sec if row_sec else None,
                               "achieved_Gmadd_s_per_gpu": (row_madds * rows / row_sec / 1e9) if row_sec else None,
-                              "fp32_fma_peak_Gmadd_s": 37000},
+                              "fp32_fma_peak_Gmadd_s": 37000,
+                              "bytes_read_per_row_all_plans": row_slice_bytes,
+                              "slice_traffic_GBs_per_gpu": (row_slice_bytes * rows / row_sec / 1e9) if row_sec else None,
+                              "slice_traffic_frac_of_hbm_peak": (row_slice_bytes * rows / row_sec / 1e9 / env.peak) if row_sec else None,
+                              "note": "a per-row plan reads, for every evidence row, one contiguous slice of each static table (the cells left "
+                                      "after fixing the row's evidence codes: 24-4866 floats per table set) from L2 / HBM: that slice traffic, not the "
+                                      "|E| + 4*card_T bytes of the gather plans, is what the executor moves"},
             "roofline": roofline(env, alg, sec, "gather_* + ve_rows_* over the compiled patterns",
                                  extra={"bound_note": "compute-shaped: the per-row plans eliminate 1-9 hidden variables per row; see per_row_plans.achieved_Gmadd_s_per_gpu"})}
 

@@ -212,7 +212,7 @@ def test_contraction_kernel_on_large_outputs():
     names = [f"v{i}" for i in range(len(cards))]
     t = DiscreteTables(names, {}, device=DEV)
     t.set_cards(cards)
-    c = VECompiler(t)
+    c = VECompiler(t, rescale=False)                                # the raw kernel; the rescaled variant is checked below
     g = torch.Generator(device=DEV); g.manual_seed(4)
     a_scope, b_scope = [0, 2, 4, 7, 10], [1, 3, 5, 6, 8, 9, 10]
     A = torch.rand([cards[v] for v in a_scope], device=DEV, generator=g)
@@ -225,6 +225,14 @@ def test_contraction_kernel_on_large_outputs():
     expr = "".join(letters[v] for v in a_scope) + "," + "".join(letters[v] for v in b_scope) + "->" + "".join(letters[v] for v in out_scope)
     want = torch.einsum(expr, A, B).reshape(-1)
     assert got.numel() == n_out
+    # range control: with variable 7 (the slowest output axis) declared an evidence axis, every one of its 255 slices is
+    # divided by its own maximum (cbn_factor_rescale) -- bit-equal to the division done by torch
+    cr = VECompiler(t)
+    cr._ev_set = {7}
+    scaled = cr._contract([Factor(a_scope, A.reshape(-1)), Factor(b_scope, B.reshape(-1))], out_scope, 10, dry=False).tensor
+    w2 = want.view(255, -1)
+    torch.testing.assert_close(scaled.view(255, -1), w2 * (1.0 / w2.max(dim=1, keepdim=True).values), rtol=1e-6, atol=0)
+    del scaled, w2
     torch.testing.assert_close(got, want, rtol=1e-6, atol=0)
     del got, want
     torch.cuda.empty_cache()
