@@ -408,7 +408,7 @@ __device__ __noinline__ uint4 exact_index4(const GTable& T, const Loader& L, int
 template <int CT, typename Loader>
 __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int n_tables, const float* __restrict__ pool,
                                              const Loader& L, int64_t quad, int64_t n_rows, const GatherOuts& outs,
-                                             uint64_t st_pol = 0) {
+                                             uint64_t st_pol = 0, uint64_t ld_pol = 0) {
   float p[4][CT];
   uint32_t bad = 0, ibad = 0;
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
@@ -479,7 +479,15 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         float v[CT];
-        load_slice<CT>(base + idx[r], v);
+        if (CT == 4 && ld_pol && T.smem_off < 0) {
+          // a large table in global memory: keep it in L2 (evict-last) while the code and posterior streams pass through
+          float4 a;
+          asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(base + idx[r]), "l"(ld_pol));
+          v[0] = a.x; v[1 % CT] = a.y; v[2 % CT] = a.z; v[3 % CT] = a.w;
+        } else {
+          load_slice<CT>(base + idx[r], v);
+        }
 #pragma unroll
         for (int t = 0; t < CT; ++t) p[r][t] *= v[t];
       }
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned
         const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
         gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs, st_pol, ld_pol);
       } else {
-        gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs, st_pol);
+        gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs, st_pol, ld_pol);
       }
     }
     __syncwarp();
@@ -977,9 +985,17 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// units of work (256-thread quads blocks, or tiles) over at most `cap` resident CTAs: when one wave is not enough, the
+// grid is shrunk so that every CTA gets the same number of rounds (1024 units on 740 slots: 512 CTAs x 2 rounds instead
+// of 740 CTAs of which 284 do a second round while the others idle)
+int64_t balanced_grid(int64_t units, int64_t cap) {
+  if (units <= cap) return std::max<int64_t>(units, 1);
+  const int64_t rounds = (units + cap - 1) / cap;
+  return (units + rounds - 1) / rounds;
+}
 int gather_blocks(cbn_ctx* ctx, int64_t n_rows, int per_sm) {
   const int64_t nquads = (n_rows + 3) >> 2;
-  return (int)std::max<int64_t>(1, std::min<int64_t>((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * per_sm));
+  return (int)balanced_grid((nquads + GATHER_TPB - 1) / GATHER_TPB, int64_t(ctx->sm_count) * per_sm);
 }
 template <int CT>
 int launch_codes(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
@@ -1067,7 +1083,7 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   }
   const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
   const int per_sm = p->occ[1];
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, int64_t(ctx->sm_count) * per_sm));
+  const int blocks = (int)balanced_grid(n_tiles, int64_t(ctx->sm_count) * per_sm);
   CBN_CUDA(ctx, launch_pdl(gather_tiles_kernel<CT, NOUT>, blocks, GATHER_TPB, smem, s, p->d_blob, (int)p->blob_bytes,
                            (int)p->desc_bytes, p->n_tables, cols, n_stages, hints, ev, ld, n_rows, p->static_evidence, outs));
   return CBN_OK;
@@ -1085,6 +1101,9 @@ bool use_tiles(const cbn_ve_plan* p, int64_t n_rows, bool force = false) {
       if (!seen[t.slot[j]]) { seen[t.slot[j]] = 1; ++n; }
   if (n < 1 || n > GT_MAX_COLS) return false;
   if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS > 150 * 1024) return false;
+  // large tables in global memory (not staged): the tile-staged kernel carries the L2 policies that keep the table
+  // resident while the streams pass through, which pays from a few hundred thousand rows on
+  if (!p->staged && p->table_bytes >= (4ll << 20) && n_rows >= (int64_t(1) << 18)) return true;
   return force || mode == 1 || n_rows >= (int64_t(1) << 21);
 }
 

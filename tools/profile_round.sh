@@ -1,14 +1,17 @@
 #!/bin/bash
-# ncu evidence for profiles/: run only after the plain commands have exited 0 (numbers printed under ncu are not bench values)
-set -x
+# ncu evidence for profiles/ (round 2): run only after the plain commands have exited 0 (numbers printed under ncu are not bench values)
 OUT=gpurun_out
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > $OUT/plain_r1e.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_r1e.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > $OUT/ncu_launch_r1e.log 2>&1
-python tools/bench_kernels.py gather --ncu-friendly > $OUT/plain_bk_gather.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:gather_inter_kernel --launch-skip 4 -c 1 -o /tmp/p_gather_asia python tools/bench_kernels.py gather --ncu-friendly > $OUT/ncu_g1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gather_tiles_kernel --launch-skip 2 -c 1 -o /tmp/p_gather_alarm python tools/bench_kernels.py gather --ncu-friendly > $OUT/ncu_g2.log 2>&1
-python tools/bench_kernels.py count --ncu-friendly > $OUT/plain_bk_count.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:count_tiles_kernel -c 15 -o /tmp/p_count python tools/bench_kernels.py count --ncu-friendly > $OUT/ncu_c1.log 2>&1
-for f in p_gather_asia p_gather_alarm p_count; do python tools/ncu_summary.py /tmp/$f.ncu-rep > $OUT/sum_$f.txt 2>&1; done
-cp /tmp/p_gather_asia.ncu-rep /tmp/p_gather_alarm.ncu-rep $OUT/ 2>/dev/null
-ls -la /tmp/*.ncu-rep $OUT
+mkdir -p $OUT
+HEAD="python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline"
+$HEAD > $OUT/plain_head.log 2>&1 || exit 1
+# every launch of the headline leg with its device time (shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_r2.csv $HEAD > $OUT/ncu_launch_r2.log 2>&1
+# the dominant kernel, 3 consecutive launches out of the timed graph: DRAM bytes per launch, stalls
+ncu --set full --clock-control none --import-source on -k regex:gather_tiles_kernel -s 40 -c 3 -o $OUT/prof_gather_alarm_r2 $HEAD > $OUT/ncu_head_r2.log 2>&1
+python tools/count_one.py ktree200 25 3 > $OUT/plain_count.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:count_tiles -s 2 -c 1 -o $OUT/prof_count_ktree_r2 python tools/count_one.py ktree200 25 3 > $OUT/ncu_count_r2.log 2>&1
+python tools/count_one.py alarm 26 3 >> $OUT/plain_count.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:count_tiles -s 2 -c 1 -o $OUT/prof_count_alarm_r2 python tools/count_one.py alarm 26 3 >> $OUT/ncu_count_r2.log 2>&1
+python tools/exp_rows_one.py 28 > $OUT/plain_rows.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:ve_rows -s 2 -c 1 -o $OUT/prof_rows28_r2 python tools/exp_rows_one.py 28 > $OUT/ncu_rows_r2.log 2>&1
+ls -la $OUT/*.ncu-rep
