@@ -160,13 +160,17 @@ class BayesianNetwork:
         return self.nodes_obj[target_node].get_prob(query, N_max)
 
     def infer(self, target_node: str, evidence: Dict[str, torch.Tensor] = None, do: List[str] = None,
-              N_max: int = 16, plot_prob=False, normalization: str = None):
+              N_max: int = 16, plot_prob=False, normalization: str = None, pad_to_N_max: bool = False):
         """
         :param target_node: node whose posterior is computed
         :param evidence: name -> tensor [n_queries, 1] of observed VALUES
         :param do: names of evidence variables that are interventions
         :param N_max: number of evaluation points of the target domain (reference semantics, node.py:286-300):
                       ``N_max >= card(target)`` evaluates the whole domain, smaller values sub-sample it
+        :param pad_to_N_max: reproduce the reference's output SHAPE for ``N_max > card(target)``: the domain is padded to
+                      N_max points with never-observed values (``Node.sample_domain``, deterministic here) whose
+                      probability is zero, so ``pdf`` and ``domains`` are ``[n_queries, N_max]`` as in the reference
+                      (node.py:302-333).  Off by default: the posterior then has ``card(target)`` columns.
         :return: (pdf [n_queries, V], domains [n_queries, V])
         """
         if target_node not in self.nodes_obj:
@@ -178,6 +182,12 @@ class BayesianNetwork:
             idx = torch.linspace(0, dom.shape[0] - 1, N_max).round().long().to(dom.device)
             pdf = pdf[:, idx].contiguous()
             dom = dom[idx]
+        elif pad_to_N_max and N_max > dom.shape[0]:
+            padded = self.nodes_obj[target_node].sample_domain(target_node, N_max).to(dom.device)
+            pos = torch.searchsorted(padded, dom)                      # where the fitted values sit in the padded domain
+            wide = torch.zeros((pdf.shape[0], N_max), dtype=pdf.dtype, device=pdf.device)
+            wide[:, pos] = pdf
+            pdf, dom = wide, padded
         domains = dom.unsqueeze(0).expand(pdf.shape[0], -1)
         assert pdf.shape == domains.shape, "pdf and domain must have same shape."
         return pdf, domains

@@ -80,6 +80,12 @@ def test_wide_target_through_the_network_api(golden_dir):
     np.testing.assert_allclose(pdf.cpu().numpy(), post[:, r_code].T, rtol=1e-5, atol=1e-12)
     m = bn.infer_map("obs_0", ev)
     assert np.array_equal(m.cpu().numpy(), dom[0].cpu().numpy()[post[:, r_code].argmax(0)])
+    # the reference's output shape for N_max > card: the domain padded to N_max never-observed points of probability zero
+    wide, wdom = bn.infer("obs_0", ev, N_max=16, pad_to_N_max=True)
+    assert wide.shape == (777, 16) and wdom.shape == (777, 16)
+    assert bool((wdom[0, 1:] > wdom[0, :-1]).all())                                   # sorted, distinct
+    keep = torch.isin(wdom[0], dom[0])
+    assert int(keep.sum()) == 11 and torch.equal(wide[:, keep], pdf) and float(wide[:, ~keep].abs().max()) == 0.0
     pred = bn.benchmarking_df(df.iloc[:300], "obs_0", batch_size=128)
     assert pred.shape == (300,) and set(np.unique(pred)) <= set(g["domain_obs_0"].tolist())
     # 16-value target, 2 evidence parents, synthetic
