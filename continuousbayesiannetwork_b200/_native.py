@@ -50,6 +50,7 @@ class Contract(C.Structure):
         ("sum_stride", C.c_int32 * MAX_CONTRACT_INPUTS),
         ("out", C.c_void_p),
         ("normalize_last", C.c_int32),
+        ("log_space", C.c_int32),
     ]
 
 
@@ -86,6 +87,7 @@ class RowStep(C.Structure):
 
 
 ROWS_LOG_SPACE = 1
+GATHER_NORMALIZE, GATHER_LOG_SPACE = 1, 2
 COMM_ID_BYTES = 128
 
 # name -> (restype, argtypes); also the list the CPU test checks against the header
@@ -118,7 +120,7 @@ SIGNATURES = {
     "cbn_get_prob_f32": (C.c_int, [_P, _P, C.POINTER(Family), C.POINTER(_P), _P, C.c_int64, C.c_int32, _P,
                                    C.c_int64, _P, _P]),
     "cbn_factor_contract": (C.c_int, [_P, C.POINTER(Contract), _P]),
-    "cbn_factor_rescale": (C.c_int, [_P, _P, C.c_longlong, C.c_int32, _P]),
+    "cbn_factor_rescale": (C.c_int, [_P, _P, C.c_longlong, C.c_int32, C.c_int32, _P]),
     "cbn_ve_plan_create_gather": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(GatherTable),
                                             C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "cbn_ve_plan_create_rows": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(RowInput), C.c_int32,

@@ -18,7 +18,15 @@ namespace {
 // and a shift per axis instead of a 64-bit division.
 struct ContractMagic { unsigned long long m[CBN_MAX_CONTRACT_DIMS]; int sh[CBN_MAX_CONTRACT_DIMS]; };
 
-template <bool FAST>
+// log-sum-exp of two log values (either may be -inf)
+__device__ __forceinline__ float lse_pair(float a, float b) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  return (hi == NEG_INF) ? NEG_INF : hi + log1pf(expf(lo - hi));
+}
+
+// LOG: the tables hold logarithms -- products are sums, the sum over the eliminated variable is a log-sum-exp
+template <bool FAST, bool LOG>
 __global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ cbn_contract d, const __grid_constant__ ContractMagic mg,
                                                        long long n_out) {
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
@@ -46,22 +54,33 @@ __global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ c
           if (k < d.n_in) base[k] += (long long)c * d.in_stride[k][a];
       }
     }
-    float acc = 0.0f;
+    float acc = LOG ? __int_as_float(0xff800000) : 0.0f;
     for (int s = 0; s < d.sum_card; ++s) {
-      float prod = 1.0f;
+      float prod = LOG ? 0.0f : 1.0f;
 #pragma unroll
       for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
-        if (k < d.n_in) prod *= __ldg(d.in[k] + base[k] + (long long)s * d.sum_stride[k]);
-      acc += prod;
+        if (k < d.n_in) {
+          const float x = __ldg(d.in[k] + base[k] + (long long)s * d.sum_stride[k]);
+          prod = LOG ? prod + x : prod * x;
+        }
+      acc = LOG ? lse_pair(acc, prod) : acc + prod;
     }
     d.out[o] = acc;
   }
 }
 
+// LOG: the slice holds logarithms; the result is the LINEAR normalised distribution (softmax), zeros for an all -inf slice
+template <bool LOG>
 __global__ void __launch_bounds__(256) normalize_last_kernel(float* x, long long n_rows, int card) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
        r += (long long)gridDim.x * blockDim.x) {
     float* p = x + r * card;
+    if (LOG) {
+      float m = __int_as_float(0xff800000);
+      for (int t = 0; t < card; ++t) m = fmaxf(m, p[t]);
+      const bool dead = m == __int_as_float(0xff800000);
+      for (int t = 0; t < card; ++t) p[t] = dead ? 0.0f : expf(p[t] - m);
+    }
     float z = 0.0f;
     for (int t = 0; t < card; ++t) z += p[t];
     const float inv = z > 0.0f ? 1.0f / z : 0.0f;
@@ -70,28 +89,36 @@ __global__ void __launch_bounds__(256) normalize_last_kernel(float* x, long long
 }
 // every slice (n_slices contiguous runs of slice_size cells) is divided by its maximum; all-zero slices stay zero.
 // One warp per slice, lanes strided over the cells.
+template <bool LOG>
 __global__ void __launch_bounds__(256) rescale_slices_kernel(float* __restrict__ x, long long n_slices, int slice_size) {
+  const float NEG_INF = __int_as_float(0xff800000);
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long sl = warp0; sl < n_slices; sl += n_warps) {
     float* p = x + sl * slice_size;
-    float m = 0.0f;
+    float m = LOG ? NEG_INF : 0.0f;
     for (int i = lane; i < slice_size; i += 32) m = fmaxf(m, p[i]);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (m > 0.0f && m != 1.0f) {
+    if (LOG) {
+      if (m != NEG_INF && m != 0.0f) for (int i = lane; i < slice_size; i += 32) p[i] -= m;
+    } else if (m > 0.0f && m != 1.0f) {
       const float inv = 1.0f / m;
       for (int i = lane; i < slice_size; i += 32) p[i] *= inv;
     }
   }
 }
 // slices of at most 8 cells: one thread per slice
+template <bool LOG>
 __global__ void __launch_bounds__(256) rescale_small_slices_kernel(float* __restrict__ x, long long n_slices, int slice_size) {
+  const float NEG_INF = __int_as_float(0xff800000);
   for (long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x; sl < n_slices; sl += (long long)gridDim.x * blockDim.x) {
     float* p = x + sl * slice_size;
-    float m = 0.0f;
+    float m = LOG ? NEG_INF : 0.0f;
     for (int i = 0; i < slice_size; ++i) m = fmaxf(m, p[i]);
-    if (m > 0.0f && m != 1.0f) {
+    if (LOG) {
+      if (m != NEG_INF && m != 0.0f) for (int i = 0; i < slice_size; ++i) p[i] -= m;
+    } else if (m > 0.0f && m != 1.0f) {
       const float inv = 1.0f / m;
       for (int i = 0; i < slice_size; ++i) p[i] *= inv;
     }
@@ -99,7 +126,8 @@ __global__ void __launch_bounds__(256) rescale_small_slices_kernel(float* __rest
 }
 }  // namespace
 
-extern "C" int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, cbn_stream stream) {
+extern "C" int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, int32_t log_space,
+                                  cbn_stream stream) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_factor_rescale: ctx is NULL");
   if (!table || n_slices < 0 || slice_size < 1) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_factor_rescale: bad argument");
   if (n_slices == 0) return CBN_OK;
@@ -107,10 +135,12 @@ extern "C" int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices
   cudaStream_t s = (cudaStream_t)stream;
   if (slice_size <= 8) {
     const int blocks = (int)std::min<long long>((n_slices + 255) / 256, (long long)ctx->sm_count * 16);
-    rescale_small_slices_kernel<<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+    if (log_space) rescale_small_slices_kernel<true><<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+    else rescale_small_slices_kernel<false><<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
   } else {
     const int blocks = (int)std::min<long long>((n_slices + 7) / 8, (long long)ctx->sm_count * 16);
-    rescale_slices_kernel<<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+    if (log_space) rescale_slices_kernel<true><<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
+    else rescale_slices_kernel<false><<<blocks, 256, 0, s>>>(table, n_slices, slice_size);
   }
   CBN_CHECK_LAUNCH(ctx);
   return CBN_OK;
@@ -142,14 +172,16 @@ extern "C" int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_s
     mg.sh[a] = 32 + L;
     mg.m[a] = ((1ull << mg.sh[a]) + card - 1) / card;
   }
-  if (fast) contract_kernel<true><<<blocks, 256, 0, s>>>(*desc, mg, n_out);
-  else contract_kernel<false><<<blocks, 256, 0, s>>>(*desc, mg, n_out);
+  const bool lg = desc->log_space != 0;
+  if (fast) { if (lg) contract_kernel<true, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<true, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
+  else { if (lg) contract_kernel<false, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<false, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
   CBN_CHECK_LAUNCH(ctx);
   if (desc->normalize_last && desc->n_out_dims > 0) {
     int card = desc->out_card[desc->n_out_dims - 1];
     long long rows = n_out / card;
     int b2 = (int)std::min<long long>((rows + 255) / 256, (long long)ctx->sm_count * 16);
-    normalize_last_kernel<<<b2, 256, 0, s>>>(desc->out, rows, card);
+    if (lg) normalize_last_kernel<true><<<b2, 256, 0, s>>>(desc->out, rows, card);
+    else normalize_last_kernel<false><<<b2, 256, 0, s>>>(desc->out, rows, card);
     CBN_CHECK_LAUNCH(ctx);
   }
   return CBN_OK;
@@ -182,6 +214,7 @@ static_assert(sizeof(GTable) % 16 == 0, "GTable is copied with 128-bit loads");
 struct GatherOuts {
   float* out[GATHER_MAX_OUT];
   unsigned normalize_mask;
+  int log_space;                // the plan's tables hold logarithms: factors are added, rows go through exp(x - max) before normalising
   // MAP mode (single-target plans): instead of the posterior row, store the domain value of its largest entry in
   // out[0][row] (first maximum on ties, like argmax; an all-zero row gives the first domain value)
   const float* map_domain;
@@ -195,6 +228,7 @@ struct cbn_ve_plan {
   int n_tables = 0;
   int n_out = 1;
   unsigned normalize_mask = 1;
+  int log_space = 0;             // gather plans: tables are logarithms (cbn_ve_plan_create_gather, flag bit 1)
   std::vector<int> ev_cards;
   std::vector<GTable> h_tables;  // host copy, used to fuse plans
   // per-row elimination plans (kind == 1)
@@ -306,8 +340,19 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 template <int CT>
 __device__ __forceinline__ void finish_rows4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad,
-                                             int64_t n_rows, float* __restrict__ out, uint64_t st_pol = 0) {
+                                             int64_t n_rows, float* __restrict__ out, uint64_t st_pol = 0, bool log_space = false) {
   pdl_wait();
+  if (log_space) {      // logs -> linear, scaled so that the row maximum is 1 (an all -inf row becomes zeros)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float m = p[r][0];
+#pragma unroll
+      for (int t = 1; t < CT; ++t) m = fmaxf(m, p[r][t]);
+      const bool dead = m == __int_as_float(0xff800000);
+#pragma unroll
+      for (int t = 0; t < CT; ++t) p[r][t] = dead ? 0.0f : __expf(p[r][t] - m);
+    }
+  }
   if (normalize) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -385,7 +430,7 @@ template <int CT>
 __device__ __forceinline__ void finish_any4(float (&p)[4][CT], uint32_t bad, bool normalize, int64_t quad, int64_t n_rows,
                                             const GatherOuts& outs, int which, uint64_t st_pol) {
   if (outs.map_domain) finish_map4<CT>(p, bad, quad, n_rows, outs.map_domain, outs.out[which]);
-  else finish_rows4<CT>(p, bad, normalize, quad, n_rows, outs.out[which], st_pol);
+  else finish_rows4<CT>(p, bad, normalize, quad, n_rows, outs.out[which], st_pol, outs.log_space != 0);
 }
 
 // exact 32-bit index + unseen flags of one table for 4 rows (used when a code >= 128 shows up)
@@ -413,6 +458,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
   uint32_t bad = 0, ibad = 0;
   uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;
   int cur = -1, n_mul = 0;
+  const bool lg = outs.log_space != 0;
   for (int k = 0; k < n_tables; ++k) {
     const GTable& T = st[k];
     const int flags = T.flags;
@@ -424,7 +470,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int t = 0; t < CT; ++t) p[r][t] = 1.0f;
+        for (int t = 0; t < CT; ++t) p[r][t] = lg ? 0.0f : 1.0f;
     }
     if (!(flags & GT_SAME_INDEX)) {
       const int mode = flags >> GT_MODE_SHIFT;
@@ -489,11 +535,11 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
           load_slice<CT>(base + idx[r], v);
         }
 #pragma unroll
-        for (int t = 0; t < CT; ++t) p[r][t] *= v[t];
+        for (int t = 0; t < CT; ++t) p[r][t] = lg ? p[r][t] + v[t] : p[r][t] * v[t];
       }
       // range control: every table slice is scaled to maximum 1 at compile time; a long product of such slices is
       // pulled back to maximum 1 every fourth factor (a per-row constant, it cancels in the normalisation)
-      if ((++n_mul & 3) == 0) {
+      if (!lg && (++n_mul & 3) == 0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           float m = p[r][0];
@@ -509,7 +555,7 @@ __device__ __forceinline__ void gather_rows4(const GTable* __restrict__ st, int 
       for (int r = 0; r < 4; ++r) {
         const float s = base[idx[r]];
 #pragma unroll
-        for (int t = 0; t < CT; ++t) p[r][t] *= s;
+        for (int t = 0; t < CT; ++t) p[r][t] = lg ? p[r][t] + s : p[r][t] * s;
       }
     }
   }
@@ -770,7 +816,8 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTa
     while (k < n_tables) {
       const int cur = g_tables[k].out_id;
       float* dst = outs.out[cur] + row * card_t;
-      for (int t = 0; t < card_t; ++t) dst[t] = 1.0f;
+      const bool lg = outs.log_space != 0;
+      for (int t = 0; t < card_t; ++t) dst[t] = lg ? 0.0f : 1.0f;
       bool bad = false;
       for (; k < n_tables && g_tables[k].out_id == cur; ++k) {
         const GTable& T = g_tables[k];
@@ -782,8 +829,14 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_codes_wide_kernel(const GTa
           idx += c * (uint32_t)T.stride[j];
         }
         idx = min(idx, (uint32_t)T.n_cells - (has_t ? card_t : 1));
-        if (has_t) for (int t = 0; t < card_t; ++t) dst[t] *= __ldg(T.data + idx + t);
-        else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] *= s; }
+        if (has_t) for (int t = 0; t < card_t; ++t) { const float v = __ldg(T.data + idx + t); dst[t] = lg ? dst[t] + v : dst[t] * v; }
+        else { float s = __ldg(T.data + idx); for (int t = 0; t < card_t; ++t) dst[t] = lg ? dst[t] + s : dst[t] * s; }
+      }
+      if (lg) {
+        float m = dst[0];
+        for (int t = 1; t < card_t; ++t) m = fmaxf(m, dst[t]);
+        const bool dead = m == __int_as_float(0xff800000);
+        for (int t = 0; t < card_t; ++t) dst[t] = dead ? 0.0f : __expf(dst[t] - m);
       }
       float inv = 1.0f;
       if ((outs.normalize_mask >> cur) & 1u) {
@@ -880,7 +933,9 @@ extern "C" int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const
   cbn_ve_plan* p = new (std::nothrow) cbn_ve_plan();
   if (!p) return cbn_fail(ctx, CBN_ERR_NOMEM, "out of host memory");
   p->device = ctx->device; p->n_evidence = n_evidence; p->card_t = card_t;
-  p->n_out = 1; p->normalize_mask = normalize ? 1u : 0u;
+  p->n_out = 1; p->normalize_mask = (normalize & 1) ? 1u : 0u;
+  p->log_space = (normalize & 2) ? 1 : 0;
+  if (p->log_space && !(normalize & 1)) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_gather: log-space tables need the normalising epilogue"); }
   p->ev_cards.assign(ev_cards, ev_cards + n_evidence);
   p->h_tables = h;
   int rc = finalize_plan(ctx, p, (cudaStream_t)stream);
@@ -903,10 +958,10 @@ extern "C" int cbn_ve_plan_fuse(cbn_ctx* ctx, const cbn_ve_plan* const* plans, i
     const cbn_ve_plan* q = plans[i];
     if (!q) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plan %d is NULL", i); }
     if (q->kind != 0) { delete p; return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: per-row plans cannot be fused"); }
-    if (i == 0) { p->n_evidence = q->n_evidence; p->ev_cards = q->ev_cards; p->card_t = q->card_t; }
-    if (q->ev_cards != p->ev_cards || q->card_t != p->card_t) {
+    if (i == 0) { p->n_evidence = q->n_evidence; p->ev_cards = q->ev_cards; p->card_t = q->card_t; p->log_space = q->log_space; }
+    if (q->ev_cards != p->ev_cards || q->card_t != p->card_t || q->log_space != p->log_space) {
       delete p;
-      return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plans must share the evidence list and the target cardinality");
+      return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_fuse: plans must share the evidence list, the target cardinality and the number space");
     }
     for (int o = 0; o < q->n_out; ++o) {
       if (p->n_out >= GATHER_MAX_OUT) { delete p; return cbn_fail(ctx, CBN_ERR_UNSUPPORTED, "cbn_ve_plan_fuse: at most %d targets per launch", GATHER_MAX_OUT); }
@@ -1167,6 +1222,7 @@ int check_run_args(cbn_ctx* ctx, const char* fn, const cbn_ve_plan* plan, const 
   if (plan->n_evidence > 0 && (ld < n_rows || (ld % 16) != 0 || !is_aligned(ev_codes, 16)))
     return cbn_fail(ctx, CBN_ERR_INVALID, "%s: evidence matrix needs ld >= n_rows, ld %% 16 == 0, 16-byte aligned base", fn);
   outs->normalize_mask = plan->normalize_mask;
+  outs->log_space = plan->log_space;
   for (int o = 0; o < plan->n_out; ++o) {
     if (!posteriors[o] || !is_aligned(posteriors[o], 16))
       return cbn_fail(ctx, CBN_ERR_INVALID, "%s: posterior %d must be a 16-byte aligned device pointer", fn, o);
@@ -1715,6 +1771,7 @@ extern "C" int cbn_ve_run_f32(cbn_ctx* ctx, const cbn_ve_plan* plan, const float
   GatherOuts outs{};
   outs.out[0] = posterior;
   outs.normalize_mask = plan->normalize_mask;
+  outs.log_space = plan->log_space;
   cudaStream_t s = (cudaStream_t)stream;
   switch (plan->card_t) {
     case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, outs, s);
@@ -1748,8 +1805,9 @@ extern "C" int cbn_ve_run_codes_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const
   DeviceGuard g(ctx->device);
   GatherOuts outs{};
   outs.out[0] = map_out;
-  outs.normalize_mask = 0;                 // the largest entry is the same with or without normalisation
+  outs.normalize_mask = 0;                 // the largest entry is the same with or without normalisation (and in log space)
   outs.map_domain = target_domain;
+  outs.log_space = plan->log_space;
   return ve_run_codes_impl(ctx, plan, ev_codes, ld, n_rows, outs, (cudaStream_t)stream);
 }
 
@@ -1774,6 +1832,7 @@ extern "C" int cbn_ve_run_f32_map(cbn_ctx* ctx, const cbn_ve_plan* plan, const f
   outs.out[0] = map_out;
   outs.normalize_mask = 0;
   outs.map_domain = target_domain;
+  outs.log_space = plan->log_space;
   cudaStream_t s = (cudaStream_t)stream;
   switch (plan->card_t) {
     case 1: return launch_f32<1>(ctx, plan, evp, dom_floats, n_rows, outs, s);
@@ -1877,6 +1936,7 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     GatherOuts go{};
     for (int o = 0; o < n_out; ++o) go.out[o] = (float*)ctx->io_dev_out[b] + o * out_stride;
     go.normalize_mask = plan->normalize_mask;
+    go.log_space = plan->log_space;
     rc = ve_run_codes_impl(ctx, plan, din, chunk, m, go, s);
     if (rc) return rc;
     for (int o = 0; o < n_out; ++o) {

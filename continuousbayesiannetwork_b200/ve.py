@@ -74,7 +74,7 @@ class QueryPlan:
     """A compiled (target, evidence-set) query.  Owns the final tables and the native plan."""
 
     def __init__(self, tables_owner, target: int, evidence: List[int], card_t: int, finals: List[Factor],
-                 normalize: bool, stats: PlanStats):
+                 normalize: bool, stats: PlanStats, log_space: bool = False):
         self.owner = tables_owner
         self.ctx = tables_owner.ctx
         self.device = tables_owner.device
@@ -83,6 +83,7 @@ class QueryPlan:
         self.card_t = card_t
         self.finals = finals
         self.normalize = normalize
+        self.log_space = bool(log_space)           # the final tables hold logarithms (several tables, LSE epilogue per row)
         self.stats = stats
         self.handle = None
         cards = tables_owner.cards
@@ -104,7 +105,8 @@ class QueryPlan:
         ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
         h = C.c_void_p()
         N.check(N.lib().cbn_ve_plan_create_gather(self.ctx.handle, len(self.evidence), ev_cards, card_t, arr, len(finals),
-                                                  1 if normalize else 0, N.stream_ptr(self.device), C.byref(h)), self.ctx.handle)
+                                                  (N.GATHER_NORMALIZE if normalize else 0) | (N.GATHER_LOG_SPACE if log_space else 0),
+                                                  N.stream_ptr(self.device), C.byref(h)), self.ctx.handle)
         self.handle = h
 
     def __del__(self):
@@ -456,6 +458,7 @@ class VECompiler:
         out = torch.empty(max(n_out, 1), dtype=torch.float32, device=self.t.device)
         d.out = out.data_ptr()
         d.normalize_last = 1 if normalize_last else 0
+        d.log_space = 1 if self.log_space else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         N.check(N.lib().cbn_factor_contract(self.t.ctx.handle, C.byref(d), N.stream_ptr(self.t.device)), self.t.ctx.handle)
@@ -470,7 +473,7 @@ class VECompiler:
             slice_size = max(n_out, 1) // max(n_slices, 1)
             if all(v not in self._ev_set for v in out_scope[lead:]):
                 N.check(N.lib().cbn_factor_rescale(self.t.ctx.handle, out.data_ptr(), n_slices, slice_size,
-                                                   N.stream_ptr(self.t.device)), self.t.ctx.handle)
+                                                   1 if self.log_space else 0, N.stream_ptr(self.t.device)), self.t.ctx.handle)
         e1.record()
         self._events.append((e0, e1))
         return Factor(out_scope, out)
@@ -515,6 +518,8 @@ class VECompiler:
                 continue
             scope = t.family_vars(t.names[v])
             tensor = None if dry else t.table_view(t.cond, t.names[v]).reshape(-1)
+            if tensor is not None and self.log_space:
+                tensor = torch.log(tensor)          # log 0 = -inf: a zero-probability entry stays one through sums and LSE
             factors.append(Factor(list(scope), tensor))
         hidden = [v for v in relevant if v not in Eset and v != T]
         stats.n_hidden = len(hidden)
@@ -568,7 +573,7 @@ class VECompiler:
                         res = self._eliminate(fs, [v for v in hidden if find(v) == root], sort_scope, sub, dry, T)
                         stats.contraction_madds += sub.contraction_madds
                         for r in res:
-                            if bool((r.tensor == 0).any().item()):
+                            if bool((r.tensor == (float("-inf") if self.log_space else 0)).any().item()):
                                 finals.append(r)
                     except PlanTooLarge:
                         stats.support_unchecked = True
@@ -577,8 +582,6 @@ class VECompiler:
             # the boundary is too large to tabulate: the rest of the hidden variables is eliminated per row
             stats.per_row_hidden = len(left)
             stats.final_tables = [(tuple(f.scope), f.size(cards)) for f in finals]
-            if self.log_space and not dry:
-                finals = [Factor(f.scope, torch.log(f.tensor)) for f in finals]
             stats.per_row_slice_cells = sum(int(f.size(cards) // max(1, _prod(cards[v] for v in f.scope if v in Eset))) for f in finals)
             plan = self._row_plan(T, E, finals, left, stats, dry)
             if dry:
@@ -593,14 +596,17 @@ class VECompiler:
         # a single pre-normalised target table needs no arithmetic per row
         normalize = True
         with_t = [f for f in finals if f.scope and f.scope[-1] == T]
+        log_tables = self.log_space
         if len(finals) == 1 and len(with_t) == 1:
+            # (in log space the normalising contraction returns the LINEAR distribution: the plan is an ordinary gather)
             finals = [self._contract(finals, finals[0].scope, None, dry, normalize_last=True)]
             normalize = False
+            log_tables = False
         if not with_t:
             # target independent of everything kept (cannot happen: P(T|pa) always mentions T)
             raise RuntimeError("internal: no final factor mentions the target")
         stats.contraction_gpu_ms = self._drain_events()
-        plan = QueryPlan(t, T, E, cards[T], finals, normalize, stats)
+        plan = QueryPlan(t, T, E, cards[T], finals, normalize, stats, log_space=log_tables)
         self._cache[key] = plan
         return plan
 

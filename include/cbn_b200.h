@@ -197,6 +197,8 @@ typedef struct cbn_contract {
   int32_t sum_stride[CBN_MAX_CONTRACT_INPUTS];
   float* out;
   int32_t normalize_last; /* 1: divide every slice over the LAST out dim by its sum (0 if the sum is 0) */
+  int32_t log_space;      /* 1: the tables hold logarithms -- products are sums, the sum over s is a log-sum-exp; with
+                             normalize_last the output is the LINEAR normalised distribution (softmax of the slice) */
 } cbn_contract;
 CBN_API int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stream stream);
 /* Range control of the compile-time elimination (the linear-space counterpart of working in log space): `table` holds
@@ -204,7 +206,9 @@ CBN_API int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_stre
  * its slowest axes -- and every slice is divided by its own maximum (all-zero slices stay zero).  A factor that depends on
  * evidence axes only cancels in the final normalisation over the target, so posteriors are unchanged while products of
  * many small likelihoods stay inside the fp32 range. */
-CBN_API int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, cbn_stream stream);
+/* log_space = 1: the table holds logarithms and every slice has its maximum subtracted instead. */
+CBN_API int cbn_factor_rescale(cbn_ctx* ctx, float* table, long long n_slices, int32_t slice_size, int32_t log_space,
+                       cbn_stream stream);
 
 /* A compiled query: after the hidden variables have been eliminated once with the
  * evidence variables kept as free axes, every row only gathers
@@ -221,7 +225,12 @@ typedef struct cbn_gather_table {
 } cbn_gather_table;
 
 /* Plan creation uploads descriptors (and small tables) on `stream` -- the stream the tables were produced on -- and
- * returns after that stream has drained; from then on the plan's device data is immutable. */
+ * returns after that stream has drained; from then on the plan's device data is immutable.
+ * normalize: bit 0 = normalise every row over the target (needed unless a single pre-normalised table is gathered);
+ * bit 1 (CBN_GATHER_LOG_SPACE) = the tables hold logarithms: factors are added per row and the row goes through
+ * exp(x - max) before it is normalised (the log-sum-exp schedule; requires bit 0). */
+#define CBN_GATHER_NORMALIZE 1
+#define CBN_GATHER_LOG_SPACE 2
 CBN_API int cbn_ve_plan_create_gather(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                               const cbn_gather_table* tables, int32_t n_tables, int32_t normalize,
                               cbn_stream stream, cbn_ve_plan** out);

@@ -306,6 +306,64 @@ def test_zero_probability_and_unseen_evidence_give_zero_rows():
     assert np.all(got[0] == 0) and np.all(got[2] == 0)
 
 
+def test_log_space_schedule_matches_linear_and_oracle():
+    """north_star (1): the whole schedule in log space -- log CPTs, factor products as sums, sum-outs as log-sum-exp at
+    compile time (cbn_factor_contract with log_space), log tables gathered and pushed through exp(x - max) per row
+    (CBN_GATHER_LOG_SPACE) -- against the fp64 oracle, the oracle's own log-space mode and the linear engine, on Asia
+    (deterministic OR node: exact zeros = -inf), Alarm (multi-table plans via a small merge budget) and a random DAG with
+    zero-probability evidence."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import bind_inference, install_cpts
+
+    spec = synth.asia()
+    tables, lin = install_cpts(spec, DEV)
+    lg = bind_inference(tables, log_space=True)
+    lg_multi = bind_inference(tables, log_space=True, merge_budget_cells=4)
+    net = _net(spec)
+    rng = np.random.default_rng(12)
+    for target, names in (("lung", ["asia", "smoke", "xray", "dysp"]), ("either", ["xray", "asia"]), ("smoke", ["lung", "dysp"]),
+                          ("tub", ["either", "xray", "dysp", "smoke"]), ("bronc", [])):
+        ev = rng.integers(0, 2, size=(67, len(names)))
+        ids = [spec.names.index(e) for e in names]
+        want = O.ve_posterior(net, spec.names.index(target), ids, ev, dtype=torch.float64)
+        want_log = O.ve_posterior(net, spec.names.index(target), ids, ev, log_space=True)
+        for eng in (lg, lg_multi):
+            plan = eng.plan(target, names)
+            got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+            np.testing.assert_allclose(got, want_log, rtol=2e-5, atol=1e-30)
+        np.testing.assert_allclose(lin.plan(target, names).run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy(), got, rtol=RTOL, atol=1e-30)
+    assert lg_multi.plan("lung", ["asia", "smoke", "xray", "dysp"]).log_space            # several log tables, LSE epilogue
+    assert not lg.plan("lung", ["asia", "smoke", "xray", "dysp"]).log_space              # one table: normalised to linear at compile time
+    # Alarm: fused launch of multi-table log plans, and MAP through the log epilogue
+    spec = synth.alarm()
+    tables, lin = install_cpts(spec, DEV)
+    lg = bind_inference(tables, log_space=True, merge_budget_cells=1 << 10)
+    codes = synth.sample_forward_numpy(spec, 21, 0, 1537)
+    ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
+    ev = codes[ids].T
+    dev_ev = _codes_matrix(ev)
+    fused = lg.fused_plan(synth.ALARM_TARGETS, synth.ALARM_EVIDENCE).run_codes(dev_ev, ev.shape[0])
+    for tg, fo in zip(synth.ALARM_TARGETS, fused):
+        plan = lg.plan(tg, synth.ALARM_EVIDENCE)
+        assert plan.log_space and len(plan.finals) > 1
+        want = O.ve_posterior(_net(spec), spec.names.index(tg), ids, ev, dtype=torch.float64)
+        np.testing.assert_allclose(fo.cpu().numpy(), want, rtol=RTOL, atol=1e-30)
+        m = plan.run_codes_map(dev_ev, ev.shape[0]).cpu().numpy()
+        assert np.array_equal(m, want.argmax(1).astype(np.float32))
+    # zero-probability evidence in log space: all -inf rows become all-zero rows
+    names = ["a", "b", "c"]
+    cpts = [np.array([0.5, 0.5]), np.array([[1.0, 0.0], [0.3, 0.7]]), np.array([[0.2, 0.8], [0.0, 1.0]])]
+    spec = synth.NetSpec(names, [2, 2, 2], [[], [0], [1]], cpts)
+    tables, _ = install_cpts(spec, DEV)
+    lg = bind_inference(tables, log_space=True, merge_budget_cells=2)
+    ev = np.array([[0, 0], [1, 0], [1, 1], [0, 1]])                 # (b, c): c=0 given b=1 has probability 0
+    want = O.ve_posterior(_net(spec), 0, [1, 2], ev, dtype=torch.float64)
+    got = lg.plan("a", ["b", "c"]).run_codes(_codes_matrix(ev), 4).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
+    assert got[1].sum() == 0.0
+
+
 def test_long_products_of_small_likelihoods_do_not_underflow():
     """Range control of the linear-space path (the alternative to log space): a binary cause with 22 observed binary
     effects whose observed values have likelihoods of 1e-3 / 3e-3 -- the all-ones configuration has probability ~1e-60,
@@ -332,7 +390,9 @@ def test_long_products_of_small_likelihoods_do_not_underflow():
     want = O.ve_posterior(net, 0, list(range(1, n_e + 1)), ev, dtype=torch.float64)
     assert want[0, 0] < 1e-9 and want[0].sum() > 0.999           # the oracle itself resolves the tiny posterior
     tables, infer = install_cpts(spec, DEV)
-    variants = {"merged": infer, "unmerged": bind_inference(tables, merge_budget_cells=1 << 8)}
+    variants = {"merged": infer, "unmerged": bind_inference(tables, merge_budget_cells=1 << 8),
+                "log_space_merged": bind_inference(tables, log_space=True),
+                "log_space_unmerged": bind_inference(tables, log_space=True, merge_budget_cells=1 << 8)}
     for label, eng in variants.items():
         got = eng.plan("T", names[1:]).run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30, err_msg=label)
