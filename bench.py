@@ -728,7 +728,7 @@ def bench_ktree200(env, args):
     torch.cuda.empty_cache()
     # ---- queries: 8 patterns = random target + 10 random evidence variables, 1,048,576 rows each (per GPU).  Every pattern
     # rotates through its own ring of distinct batches (evidence + posteriors of one batch: 26 MB; ring of 6 > L2).
-    infer = bind_inference(t)
+    infer = bind_inference(t, profile_compile=True)          # CUDA events around every contraction: contraction_gpu_ms
     rng = np.random.default_rng(1240)
     rows, n_ring = 1 << 20, 6
     fulls = [sample_network(spec, seed=1241 + r, first=rank * rows, n=rows, device=dev, tables=t) for r in range(n_ring)]

@@ -69,6 +69,69 @@ __global__ void __launch_bounds__(256) contract_kernel(const __grid_constant__ c
   }
 }
 
+// Tiled variant for large outputs: the output index is split into (o_hi, o_lo) with o_lo running over the fastest axes
+// (LO <= 1024 cells).  The per-input offsets of every o_lo are decoded ONCE per CTA into shared memory, o_hi is decoded
+// once per (CTA, o_hi) instead of once per cell, and a cell costs n_in shared-memory reads plus its table loads -- the
+// plain kernel spends most of its time on the multiply-shift decode of up to 13 axes per cell.
+template <bool LOG, int NIN>
+__global__ void __launch_bounds__(256) contract_tiled_kernel(const __grid_constant__ cbn_contract d, const __grid_constant__ ContractMagic mg,
+                                                             long long n_hi, int lo_cells, int n_lo_dims) {
+  extern __shared__ int lo_off[];          // [NIN][lo_cells]
+  const int n_hi_dims = d.n_out_dims - n_lo_dims;
+  for (int ol = threadIdx.x; ol < lo_cells; ol += blockDim.x) {
+    int off[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) off[k] = 0;
+    unsigned rem = (unsigned)ol;
+    for (int a = d.n_out_dims - 1; a >= n_hi_dims; --a) {
+      const unsigned q = (unsigned)(((unsigned long long)rem * mg.m[a]) >> mg.sh[a]);
+      const int c = (int)(rem - q * (unsigned)d.out_card[a]);
+      rem = q;
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) off[k] += c * d.in_stride[k][a];
+    }
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) lo_off[k * lo_cells + ol] = off[k];
+  }
+  __syncthreads();
+  const float* src[NIN];
+  int ss[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) { src[k] = d.in[k]; ss[k] = d.sum_stride[k]; }
+  const int sum_card = d.sum_card;
+  for (long long oh = blockIdx.x; oh < n_hi; oh += gridDim.x) {
+    long long hb[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) hb[k] = 0;
+    unsigned long long rem = (unsigned long long)oh;          // n_hi < 2^31 (checked by the host): the magic division is exact
+    for (int a = n_hi_dims - 1; a >= 0; --a) {
+      const unsigned q = (unsigned)(((unsigned long long)(unsigned)rem * mg.m[a]) >> mg.sh[a]);
+      const int c = (int)((unsigned)rem - q * (unsigned)d.out_card[a]);
+      rem = q;
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) hb[k] += (long long)c * d.in_stride[k][a];
+    }
+    float* __restrict__ out = d.out + oh * lo_cells;
+    for (int ol = threadIdx.x; ol < lo_cells; ol += blockDim.x) {
+      const float* p[NIN];
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) p[k] = src[k] + hb[k] + lo_off[k * lo_cells + ol];
+      float acc = LOG ? __int_as_float(0xff800000) : 0.0f;
+      for (int sv = 0; sv < sum_card; ++sv) {
+        float prod = LOG ? 0.0f : 1.0f;
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) {
+          const float x = __ldg(p[k]);
+          p[k] += ss[k];
+          prod = LOG ? prod + x : prod * x;
+        }
+        acc = LOG ? lse_pair(acc, prod) : acc + prod;
+      }
+      out[ol] = acc;
+    }
+  }
+}
+
 // LOG: the slice holds logarithms; the result is the LINEAR normalised distribution (softmax), zeros for an all -inf slice
 template <bool LOG>
 __global__ void __launch_bounds__(256) normalize_last_kernel(float* x, long long n_rows, int card) {
@@ -173,8 +236,36 @@ extern "C" int cbn_factor_contract(cbn_ctx* ctx, const cbn_contract* desc, cbn_s
     mg.m[a] = ((1ull << mg.sh[a]) + card - 1) / card;
   }
   const bool lg = desc->log_space != 0;
-  if (fast) { if (lg) contract_kernel<true, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<true, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
-  else { if (lg) contract_kernel<false, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<false, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
+  // large outputs with up to 4 inputs: the tiled kernel.  o_lo takes as many of the fastest axes as fit 1024 cells while
+  // at least 4 CTAs per SM worth of o_hi values remain.
+  bool tiled = false;
+  if (fast && desc->n_in <= 4 && n_out >= (1ll << 16)) {
+    long long lo = 1;
+    int nlo = 0;
+    for (int a = desc->n_out_dims - 1; a >= 0; --a) {
+      const long long next = lo * desc->out_card[a];
+      if (next > 1024 || n_out / next < (long long)ctx->sm_count * 4) break;
+      lo = next; ++nlo;
+    }
+    const long long n_hi = n_out / std::max<long long>(lo, 1);
+    if (nlo >= 1 && lo >= 32 && n_hi < (1ll << 31)) {
+      tiled = true;
+      const int tb = (int)std::min<long long>(n_hi, (long long)ctx->sm_count * 8);
+      const size_t sm = size_t(desc->n_in) * size_t(lo) * sizeof(int);
+#define CBN_TILED(L, K) contract_tiled_kernel<L, K><<<tb, 256, sm, s>>>(*desc, mg, n_hi, (int)lo, nlo)
+      switch (desc->n_in) {
+        case 1: if (lg) CBN_TILED(true, 1); else CBN_TILED(false, 1); break;
+        case 2: if (lg) CBN_TILED(true, 2); else CBN_TILED(false, 2); break;
+        case 3: if (lg) CBN_TILED(true, 3); else CBN_TILED(false, 3); break;
+        default: if (lg) CBN_TILED(true, 4); else CBN_TILED(false, 4); break;
+      }
+#undef CBN_TILED
+    }
+  }
+  if (!tiled) {
+    if (fast) { if (lg) contract_kernel<true, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<true, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
+    else { if (lg) contract_kernel<false, true><<<blocks, 256, 0, s>>>(*desc, mg, n_out); else contract_kernel<false, false><<<blocks, 256, 0, s>>>(*desc, mg, n_out); }
+  }
   CBN_CHECK_LAUNCH(ctx);
   if (desc->normalize_last && desc->n_out_dims > 0) {
     int card = desc->out_card[desc->n_out_dims - 1];

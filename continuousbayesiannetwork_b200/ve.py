@@ -389,12 +389,14 @@ class VECompiler:
     """Lower (target, evidence set) to a gather plan over a fitted ``DiscreteTables``."""
 
     def __init__(self, tables, table_budget_cells: int = 1 << 28, merge_budget_cells: int = 1 << 24,
-                 check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False, rescale: bool = True):
+                 check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False, rescale: bool = True,
+                 profile_compile: bool = False):
         self.t = tables
         # range control of the compile-time elimination: after every contraction each evidence slice of the result is
         # divided by its maximum (cbn_factor_rescale) -- a factor of the evidence configuration only, which cancels in the
         # final normalisation -- so products of many small likelihoods stay inside the fp32 range
         self.rescale = bool(rescale)
+        self.profile_compile = bool(profile_compile)      # CUDA events around every contraction -> PlanStats.contraction_gpu_ms
         self._ev_set: set = set()
         self._events: list = []
         self.table_budget = int(table_budget_cells)
@@ -459,8 +461,9 @@ class VECompiler:
         d.out = out.data_ptr()
         d.normalize_last = 1 if normalize_last else 0
         d.log_space = 1 if self.log_space else 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        if self.profile_compile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         N.check(N.lib().cbn_factor_contract(self.t.ctx.handle, C.byref(d), N.stream_ptr(self.t.device)), self.t.ctx.handle)
         if self.rescale and not normalize_last:
             # evidence axes are the slowest axes of every factor (sort_scope): one contiguous slice per evidence configuration
@@ -474,8 +477,9 @@ class VECompiler:
             if all(v not in self._ev_set for v in out_scope[lead:]):
                 N.check(N.lib().cbn_factor_rescale(self.t.ctx.handle, out.data_ptr(), n_slices, slice_size,
                                                    1 if self.log_space else 0, N.stream_ptr(self.t.device)), self.t.ctx.handle)
-        e1.record()
-        self._events.append((e0, e1))
+        if self.profile_compile:
+            e1.record()
+            self._events.append((e0, e1))
         return Factor(out_scope, out)
 
     # ---------------------------------------------------------------- compile
