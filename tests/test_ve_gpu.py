@@ -158,6 +158,81 @@ def test_config4_ktree200_tables_on_a_stratified_sample():
             np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-30)
 
 
+def test_config4_large_table_path_matches_direct_kernel():
+    """Plans whose tables live in global memory (the 16 MB tables of the 200-node patterns) switch to the tile-staged kernel
+    with L2 policies from 2^18 rows on: the same rows through the direct kernel (a batch below the threshold) must give
+    bit-identical posteriors, for a ragged row count."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts, sample_network
+
+    spec = synth.random_ktree_dag()
+    tables, infer = install_cpts(spec, DEV)
+    rng = np.random.default_rng(1240)
+    n = (1 << 18) + 37
+    full = sample_network(spec, seed=5, first=0, n=n, device=DEV, tables=tables)
+    for _ in range(2):
+        vs = [int(v) for v in rng.choice(spec.n, size=11, replace=False)]
+        plan = infer.plan(spec.names[vs[0]], [spec.names[v] for v in vs[1:]])
+        ev = full[vs[1:]].contiguous()
+        big = plan.run_codes(ev, n)                                  # tile-staged kernel
+        m = 1 << 17
+        small = plan.run_codes(ev, m)                                # direct kernel on the first 2^17 rows
+        assert torch.equal(big[:m], small)
+        start = (1 << 18) - 4096                                     # 16-byte aligned view of the ragged end
+        tail = plan.run_codes(ev[:, start:], n - start)
+        assert torch.equal(big[start:], tail)
+        assert float((big.sum(1) - 1).abs().max()) < 1e-5
+
+
+def test_random_dags_against_enumeration():
+    """Seeded sweep over 40 random small DAGs (5-10 variables, cardinalities 2-4, up to 3 parents, a third of the CPT rows
+    made deterministic so that zero-probability evidence occurs): random target / evidence / intervention sets against fp64
+    full enumeration (O3), through gather plans, the per-row executor and the log-space schedule."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import bind_inference, install_cpts
+    from continuousbayesiannetwork_b200.ve import PlanTooLarge
+
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(5, 11))
+        cards = [int(c) for c in rng.integers(2, 5, size=n)]
+        parents = [sorted(int(p) for p in rng.choice(i, size=min(i, int(rng.integers(0, 4))), replace=False)) if i else [] for i in range(n)]
+        names = [f"v{i}" for i in range(n)]
+        cpts = synth._dirichlet_cpts(rng, cards, parents, 0.7)
+        for i, c in enumerate(cpts):                                  # deterministic rows: exact zeros in the CPTs
+            flat = c.reshape(-1, cards[i])
+            for r in range(flat.shape[0]):
+                if rng.random() < 0.33:
+                    flat[r] = np.eye(cards[i])[int(rng.integers(0, cards[i]))]
+        spec = synth.NetSpec(names, cards, parents, cpts)
+        net = _net(spec)
+        tables, infer = install_cpts(spec, DEV)
+        engines = [infer, bind_inference(tables, log_space=True, merge_budget_cells=8), bind_inference(tables, table_budget_cells=1)]
+        for _ in range(3):
+            k = int(rng.integers(0, n))
+            vs = [int(v) for v in rng.choice(n, size=k + 1, replace=False)]
+            target, ev_ids = vs[0], vs[1:]
+            ev = np.stack([rng.integers(0, cards[v], size=53) for v in ev_ids], axis=1) if ev_ids else np.zeros((1, 0), dtype=np.int64)
+            truth = O.enumerate_posterior(net, target, ev_ids, ev)
+            n_checked = 0
+            for eng in engines:
+                try:
+                    plan = eng.plan(names[target], [names[v] for v in ev_ids])
+                except PlanTooLarge:                                  # the 1-cell table budget cannot merge evidence-only finals
+                    continue
+                got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
+                if plan.stats.support_unchecked:
+                    # the 1-cell budget could not tabulate the support of a component that does not contain the target (the
+                    # plan says so): rows whose evidence has probability zero are then not recognised -- compare the others
+                    keep = truth.sum(1) > 0
+                    got, want = got[keep], truth[keep]
+                else:
+                    want = truth
+                np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-12, err_msg=f"trial {trial} target {target} evidence {ev_ids}")
+                n_checked += 1
+            assert n_checked >= 2
+
+
 def test_config4_ktree200_patterns():
     """BASELINE.json configs[3], query half: 200-node card-4 partial 8-tree, random target + 10 random evidence
     variables (the 8 patterns bench.py times), against the fp32 and fp64 oracle."""
