@@ -458,6 +458,11 @@ def bench_alarm_ve(env, args):
     fused.run_codes(ev_ring[0], rows, outs=out_ring[0])
     assert torch.equal(host_out[0], out_ring[0][0].cpu()), "host-buffer call and device path disagree"
     h2d, d2h = len(evn) * ALARM_ROWS, sum(p.card_t for p in plans) * 4 * ALARM_ROWS
+    # the same call with the compact host format (CBN_HOST_OUT_DROP_LAST: card - 1 values per row travel; an API option, not
+    # the reference's output format, so it is reported beside the headline e2e, not as it)
+    host_c = [torch.empty((rows, p.card_t - 1), dtype=torch.float32).pin_memory() for p in plans]
+    c_s = env.host_timed(lambda i: fused.run_codes_host(host_ev, rows, host_c, compact=True), e2e_steps, 2)
+    assert torch.equal(host_c[0][:, 0], host_out[0][:, 0])
 
     # ---- e2e through the reference-facing Python API: infer(target, {name: float32 [nq,1]}) per target
     api_rows = min(rows, args.api_rows)
@@ -485,6 +490,9 @@ def bench_alarm_ve(env, args):
            "steps": e2e_steps, "pcie_GBs_per_gpu": (h2d + d2h) / world * e2e_steps / e2e_s / 1e9,
            "call": "cbn_ve_run_codes_host_multi (pinned host uint8 codes in, 4 pinned host fp32 posteriors out), one call per step over the rank's shard of the 16M-row batch",
            "timing": "host clock around the synchronous calls, barrier + synchronize on both sides, max over ranks",
+           "compact": {"value": ALARM_ROWS * len(tgs) * e2e_steps / c_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": sum(p.card_t - 1 for p in plans) * 4 * ALARM_ROWS,
+                       "call": "cbn_ve_run_codes_host_multi_ex(..., CBN_HOST_OUT_DROP_LAST): card - 1 probabilities per row travel to the host"},
            "python_api": {"value": api_value, "unit": "queries/s", "rows_per_gpu": api_rows,
                           "pcie_GBs_per_gpu": (4 * len(evn) * api_rows * len(tgs) + d2h // ALARM_ROWS * api_rows) * 3 / api_s / 1e9,
                           "h2d_bytes_per_step": 4 * len(evn) * api_rows * len(tgs) * world, "d2h_bytes_per_step": d2h // ALARM_ROWS * api_rows * world,
@@ -560,7 +568,7 @@ def bench_asia(env, args):
     # float32 ingestion: columns resident on the device -> domains -> codes -> counts -> CPTs (BayesianNetwork(dag, data) path)
     from continuousbayesiannetwork_b200.tables import DiscreteTables
 
-    n_in = 1 << 24
+    n_in = 1 << 26
     t0_ = tables_from_spec(spec, dev)
     c_ = sample_network(spec, seed=99, first=rank * n_in, n=n_in, device=dev, tables=t0_)
     cols = {nm: (c_[i, :n_in].to(torch.float32) * 0.5 - 1.0) for i, nm in enumerate(spec.names)}

@@ -88,6 +88,7 @@ class RowStep(C.Structure):
 
 ROWS_LOG_SPACE = 1
 GATHER_NORMALIZE, GATHER_LOG_SPACE = 1, 2
+HOST_OUT_DROP_LAST = 1
 COMM_ID_BYTES = 128
 
 # name -> (restype, argtypes); also the list the CPU test checks against the header
@@ -136,6 +137,7 @@ SIGNATURES = {
     "cbn_ve_run_f32_map": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.c_int64, _P, _P, _P]),
     "cbn_ve_run_codes_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
     "cbn_ve_run_codes_host_multi": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "cbn_ve_run_codes_host_multi_ex": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.POINTER(_P), C.c_int32]),
     "cbn_batch_max": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "cbn_scale_by_inv": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "cbn_sample_forward": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(Family), _P, C.c_uint64,

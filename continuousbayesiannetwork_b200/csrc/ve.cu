@@ -1966,8 +1966,38 @@ static int ensure_io(cbn_ctx* ctx, size_t in_bytes, size_t out_bytes) {
   return CBN_OK;
 }
 
+namespace {
+// compact posterior rows for the trip over PCIe: the last probability of a row is 1 - (sum of the others), so only the
+// first card_t - 1 values travel; an all-zero row (unseen / zero-probability evidence) is flagged by -1 in its first value
+__global__ void __launch_bounds__(256) drop_last_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n_rows, int ct) {
+  const int w = ct - 1;
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += int64_t(gridDim.x) * blockDim.x) {
+    float z = 0.0f;
+    for (int t = 0; t < ct; ++t) z += in[r * ct + t];
+    for (int t = 0; t < w; ++t) out[r * w + t] = in[r * ct + t];
+    if (!(z > 0.0f)) out[r * w] = -1.0f;
+  }
+}
+}  // namespace
+
+static int ve_run_codes_host_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                  int64_t n_rows, float* const* posteriors_host, int32_t flags);
+
 extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
                                            int64_t n_rows, float* const* posteriors_host) {
+  return ve_run_codes_host_impl(ctx, plan, ev_codes_host, ld, n_rows, posteriors_host, 0);
+}
+
+extern "C" int cbn_ve_run_codes_host_multi_ex(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                              int64_t n_rows, float* const* posteriors_host, int32_t flags) {
+  if (flags & ~CBN_HOST_OUT_DROP_LAST) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host_multi_ex: unknown flags");
+  if ((flags & CBN_HOST_OUT_DROP_LAST) && plan && plan->card_t < 2)
+    return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host_multi_ex: CBN_HOST_OUT_DROP_LAST needs a target with at least two values");
+  return ve_run_codes_host_impl(ctx, plan, ev_codes_host, ld, n_rows, posteriors_host, flags);
+}
+
+static int ve_run_codes_host_impl(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                  int64_t n_rows, float* const* posteriors_host, int32_t flags) {
   if (!ctx) return cbn_fail(nullptr, CBN_ERR_INVALID, "cbn_ve_run_codes_host: ctx is NULL");
   if (!plan || n_rows < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
   if (n_rows == 0) return CBN_OK;
@@ -1975,6 +2005,8 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: bad argument");
   if (plan->kind != 0) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: per-row plans are device-side only");
   const int n_out = plan->n_out, ct = plan->card_t;
+  const bool compact = (flags & CBN_HOST_OUT_DROP_LAST) != 0;
+  const int wo = compact ? ct - 1 : ct;          // floats per row that travel to the host
   for (int o = 0; o < n_out; ++o)
     if (!posteriors_host[o]) return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_run_codes_host: posterior %d is NULL", o);
   if (n_rows == 0) return CBN_OK;
@@ -1989,7 +2021,8 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
   const int64_t chunk = std::max<int64_t>(lead, std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 18, (((n_rows - lead) / 2 + 65535) >> 16) << 16)));
   const int ne = std::max(plan->n_evidence, 1);
   const size_t out_stride = size_t(chunk) * ct;   // floats per output inside a staging buffer
-  int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float));
+  // compact mode: the compacted rows of all outputs sit behind the full-width ones in the same device buffer
+  int rc = ensure_io(ctx, size_t(chunk) * ne, out_stride * n_out * sizeof(float) * (compact ? 2 : 1));
   if (rc) return rc;
   // Pageable or pinned caller memory: pinned callers get direct DMA, pageable ones go through pinned staging.
   cudaPointerAttributes attr{};
@@ -2001,7 +2034,7 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
   int64_t pending_row[2] = {-1, -1}, pending_m[2] = {0, 0};
   auto drain = [&](int b) {
     for (int o = 0; o < n_out; ++o)
-      memcpy(posteriors_host[o] + pending_row[b] * ct, (float*)ctx->io_pin_out[b] + o * out_stride, size_t(pending_m[b]) * ct * sizeof(float));
+      memcpy(posteriors_host[o] + pending_row[b] * wo, (float*)ctx->io_pin_out[b] + o * out_stride, size_t(pending_m[b]) * wo * sizeof(float));
   };
   int b = 0;
   for (int64_t r0 = 0, m = 0; r0 < n_rows; r0 += m, b ^= 1) {
@@ -2031,8 +2064,16 @@ extern "C" int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan
     rc = ve_run_codes_impl(ctx, plan, din, chunk, m, go, s);
     if (rc) return rc;
     for (int o = 0; o < n_out; ++o) {
-      float* dst = out_pinned ? posteriors_host[o] + r0 * ct : (float*)ctx->io_pin_out[b] + o * out_stride;
-      CBN_CUDA(ctx, cudaMemcpyAsync(dst, go.out[o], size_t(m) * ct * sizeof(float), cudaMemcpyDeviceToHost, s));
+      const float* src = go.out[o];
+      if (compact) {
+        float* cdst = (float*)ctx->io_dev_out[b] + (size_t(n_out) + o) * out_stride;
+        const int blocks = (int)std::min<int64_t>((m + 255) / 256, int64_t(ctx->sm_count) * 8);
+        drop_last_kernel<<<blocks, 256, 0, s>>>(go.out[o], cdst, m, ct);
+        CBN_CHECK_LAUNCH(ctx);
+        src = cdst;
+      }
+      float* dst = out_pinned ? posteriors_host[o] + r0 * wo : (float*)ctx->io_pin_out[b] + o * out_stride;
+      CBN_CUDA(ctx, cudaMemcpyAsync(dst, src, size_t(m) * wo * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     pending_row[b] = r0; pending_m[b] = m;
   }

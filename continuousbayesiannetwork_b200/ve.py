@@ -230,13 +230,25 @@ class FusedPlan:
         return list(outs)
 
 
-def _fused_run_codes_host(self, ev_codes_host: torch.Tensor, n_rows: int, outs_host: Sequence[torch.Tensor]):
-    """Host buffers in, host buffers out, one fused launch per chunk (copies inside; synchronous)."""
+def _fused_run_codes_host(self, ev_codes_host: torch.Tensor, n_rows: int, outs_host: Sequence[torch.Tensor], compact: bool = False):
+    """Host buffers in, host buffers out, one fused launch per chunk (copies inside; synchronous).  ``compact``: the
+    outputs are float32 [n_rows, card_t - 1] (``CBN_HOST_OUT_DROP_LAST``; ``expand_compact`` restores the full rows)."""
     assert not ev_codes_host.is_cuda and len(outs_host) == self.n_out and all(not o.is_cuda for o in outs_host)
+    width = self.card_t - 1 if compact else self.card_t
+    assert all(o.is_contiguous() and o.shape[-1] == width and o.shape[0] >= n_rows for o in outs_host)
     ptrs = N.ptr_array([o.data_ptr() for o in outs_host])
-    N.check(N.lib().cbn_ve_run_codes_host_multi(self.ctx.handle, self.handle, ev_codes_host.data_ptr(), ev_codes_host.stride(0),
-                                                int(n_rows), ptrs), self.ctx.handle)
+    N.check(N.lib().cbn_ve_run_codes_host_multi_ex(self.ctx.handle, self.handle, ev_codes_host.data_ptr(), ev_codes_host.stride(0),
+                                                   int(n_rows), ptrs, N.HOST_OUT_DROP_LAST if compact else 0), self.ctx.handle)
     return list(outs_host)
+
+
+def expand_compact(compact: torch.Tensor) -> torch.Tensor:
+    """[n, card - 1] rows of the compact host format -> full posterior rows [n, card] (last = 1 - sum; -1 flags a zero row)."""
+    dead = compact[:, 0] < 0
+    last = (1.0 - compact.sum(dim=1, keepdim=True)).clamp_(min=0.0)
+    full = torch.cat([compact, last], dim=1)
+    full[dead] = 0.0
+    return full
 
 
 FusedPlan.run_codes_host = _fused_run_codes_host

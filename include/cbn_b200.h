@@ -306,6 +306,14 @@ CBN_API int cbn_ve_run_codes_host(cbn_ctx* ctx, const cbn_ve_plan* plan, const u
 CBN_API int cbn_ve_run_codes_host_multi(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
                                 int64_t n_rows, float* const* posteriors_host);
 
+/* same, with options.  CBN_HOST_OUT_DROP_LAST: only the first card_t - 1 probabilities of every row travel to the host
+ * (posteriors_host[o] is float[n_rows, card_t - 1]; the last one is 1 minus their sum); a row that is all zeros in the
+ * full format (unseen or zero-probability evidence) carries -1 in its first value.  Halves the device->host bytes of
+ * binary targets, which is what bounds the host-buffer path. */
+#define CBN_HOST_OUT_DROP_LAST 1
+CBN_API int cbn_ve_run_codes_host_multi_ex(cbn_ctx* ctx, const cbn_ve_plan* plan, const uint8_t* ev_codes_host, int64_t ld,
+                                   int64_t n_rows, float* const* posteriors_host, int32_t flags);
+
 /* reference scaling: BayesianNetwork.infer divides the whole batch by ONE global max
  * (bayesian_network.py:296).  max_out: device float (caller zero-initialises). */
 CBN_API int cbn_batch_max(cbn_ctx* ctx, const float* x, int64_t n, float* max_out, cbn_stream stream);

@@ -558,6 +558,32 @@ def test_f32_and_host_entry_points_agree_with_codes():
     assert torch.equal(a, a[first[inv]])
 
 
+def test_compact_host_output_round_trips():
+    """CBN_HOST_OUT_DROP_LAST: card_t - 1 values per row over PCIe, -1 flags an all-zero row; expanding restores the full
+    posteriors (the last value to fp32 rounding), for binary (Asia, fused) and 4-valued targets, unseen evidence included."""
+    from continuousbayesiannetwork_b200 import synth
+    from continuousbayesiannetwork_b200.engine import install_cpts, sample_network
+    from continuousbayesiannetwork_b200.ve import FusedPlan, expand_compact
+
+    for spec, evn, tgs, n in ((synth.asia(), ["asia", "smoke", "xray", "dysp"], ["lung", "tub", "bronc"], 300_007),
+                              (synth.random_ktree_dag(n=30, card=4, k=4, max_parents=3, seed=6), None, None, 70_001)):
+        t, infer = install_cpts(spec, DEV)
+        if evn is None:
+            evn, tgs = [spec.names[i] for i in (3, 7, 11, 19)], [spec.names[25]]
+        ids = [spec.names.index(e) for e in evn]
+        ev = sample_network(spec, seed=41, first=0, n=n, device=DEV, tables=t)[ids].contiguous()
+        ev[0, 5] = 255                                               # an unseen code: all-zero row
+        fused = FusedPlan([infer.plan(tg, evn) for tg in tgs])
+        full = [o.cpu() for o in fused.run_codes(ev, n)]
+        ct = fused.card_t
+        host = [torch.full((n, ct - 1), 7.0) for _ in tgs]
+        fused.run_codes_host(ev.cpu(), n, host, compact=True)
+        for f, c in zip(full, host):
+            assert c[5, 0] == -1 and float(f[5].sum()) == 0.0
+            assert torch.equal(c[:, : ct - 1][c[:, 0] >= 0], f[:, : ct - 1][c[:, 0] >= 0])        # the values that travel are bit-equal
+            torch.testing.assert_close(expand_compact(c), f, rtol=0, atol=2e-7)
+
+
 def test_fused_multi_target_launch_matches_single_plans():
     from continuousbayesiannetwork_b200 import synth
     from continuousbayesiannetwork_b200.engine import install_cpts
