@@ -1342,10 +1342,13 @@ static_assert(sizeof(RowInputDev) % 4 == 0, "RowInputDev is staged with 32-bit c
 struct RowStepDev {
   const int* offsets;
   int out_size, sum_card, n_in, temp_off;
-  int off_at, pad;               // the step's offset table inside the plan's packed pool
+  int off_at, unit;              // the step's offset table inside the plan's packed pool; unit: see row_step_unit
   int in_id[CBN_MAX_CONTRACT_INPUTS];
   int sum_stride[CBN_MAX_CONTRACT_INPUTS];
 };
+static_assert(sizeof(RowStepDev) % 16 == 0 && sizeof(RowInputDev) % 16 == 0, "descriptors keep the shared-memory temporaries 16-byte aligned");
+constexpr int ROWS_UNIT_MAX_CARD = 8;    // widest summed variable the unrolled step bodies cover
+constexpr int ROWS_UNIT_MAX_IN = 4;      // most factors per step they cover
 
 __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -1357,11 +1360,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One warp per row.  Shared memory: [step descriptors][input descriptors][offset tables][per warp: evidence codes of
-// the row | base offsets of the static inputs | temporaries].  Everything a step needs apart from the CPT slices
-// themselves (which stay in L1/L2) is read from shared memory; the inner loops are specialised on the number of factors
-// so their pointers and offsets live in registers and the loads of one output cell are independent of each other.
-// Linear mode rescales every temporary by its maximum (a per-row constant cancels in the final normalisation), so
-// products of hundreds of CPT entries neither underflow nor need log space; LOG mode keeps logs and uses log-sum-exp.
+// the row | base offsets of the static inputs | one scale per step | temporaries].  Everything a step needs apart from
+// the CPT slices themselves (which stay in L1/L2) is read from shared memory.
+//
+// Layout contract of the fast path (RowStepDev::unit, checked at plan creation): every factor is consumed by exactly one
+// step, so the planner lays each one out with the variable THAT step sums over innermost (stride 1).  The terms of one
+// output cell are then SC consecutive floats of every factor: the step bodies are specialised on (number of factors,
+// SC), read each run with 64/128-bit loads at immediate offsets and keep the whole cell in registers -- no pointer
+// arithmetic inside the sum, no loop-carried addresses.  Steps that do not meet the contract (a C caller's own strides,
+// more than ROWS_UNIT_MAX_IN factors, a variable wider than ROWS_UNIT_MAX_CARD) take the strided bodies below.
+//
+// Range control: a temporary is stored as computed and its scale (1 / max; -max in log space) is kept per step; the
+// consuming step multiplies its finished cell by the scales of its temporaries (a per-row constant cancels in the final
+// normalisation), so products of hundreds of CPT entries do not underflow and the common case needs no rescaling pass.
+// Only a temporary whose maximum is outside [2^-12, 2^12] is rescaled in place by the step that produced it.
 template <bool LOG>
 __device__ __forceinline__ float lse2(float a, float b) {
   const float NEG_INF = __int_as_float(0xff800000);
@@ -1369,55 +1381,122 @@ __device__ __forceinline__ float lse2(float a, float b) {
   return (hi == NEG_INF) ? NEG_INF : hi + log1pf(expf(lo - hi));
 }
 
-template <bool LOG, int NIN>
-__device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* __restrict__ offs, const float* const* srcs, float* __restrict__ tout,
-                                               int lane) {
+template <int SC>
+__device__ __forceinline__ void load_run(const float* __restrict__ p, float (&x)[SC]) {
+  if constexpr (SC % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < SC / 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+  } else if constexpr (SC % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < SC / 2; ++i) {
+      const float2 v = *reinterpret_cast<const float2*>(p + 2 * i);
+      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SC; ++i) x[i] = p[i];
+  }
+}
+
+// sum over the run of the products of NIN factors (log space: log-sum-exp of the sums), scaled by the inputs' scales
+template <bool LOG, int NIN, int SC>
+__device__ __forceinline__ float cell_value(const float (&x)[NIN][SC], float scale) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  if (!LOG) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int sv = 0; sv < SC; ++sv) {
+      float q = x[0][sv];
+#pragma unroll
+      for (int k = 1; k < NIN; ++k) q *= x[k][sv];
+      acc += q;
+    }
+    return acc * scale;
+  }
+  float q[SC], m = NEG_INF;
+#pragma unroll
+  for (int sv = 0; sv < SC; ++sv) {
+    q[sv] = x[0][sv];
+#pragma unroll
+    for (int k = 1; k < NIN; ++k) q[sv] += x[k][sv];
+    m = fmaxf(m, q[sv]);
+  }
+  if (m == NEG_INF) return NEG_INF;
+  if (SC == 1) return m + scale;
+  float z = 0.0f;
+#pragma unroll
+  for (int sv = 0; sv < SC; ++sv) z += __expf(q[sv] - m);
+  return m + __logf(z) + scale;
+}
+
+template <bool LOG, int NIN, int SC>
+__device__ __forceinline__ float row_step_unit(const RowStepDev& S, const int* __restrict__ offs, const RowInputDev* __restrict__ sin,
+                                               const RowStepDev* __restrict__ sst, int n_inputs, const int* __restrict__ base,
+                                               float* temps, const float* __restrict__ tscale, int lane) {
   const float NEG_INF = __int_as_float(0xff800000);
   const float* src[NIN];
-  long long sb[NIN];           // stride of the summed variable in elements: the running pointers advance by it (one
-                               // 64-bit add per term instead of re-deriving every address from a 32-bit index)
+  float scale = LOG ? 0.0f : 1.0f;
 #pragma unroll
-  for (int k = 0; k < NIN; ++k) { src[k] = srcs[k]; sb[k] = S.sum_stride[k]; }
-  const int out_size = S.out_size, sum_card = S.sum_card;
+  for (int k = 0; k < NIN; ++k) {
+    const int id = S.in_id[k];
+    if (id < n_inputs) {
+      src[k] = sin[id].data + base[id];
+    } else {
+      src[k] = temps + sst[id - n_inputs].temp_off;
+      scale = LOG ? scale + tscale[id - n_inputs] : scale * tscale[id - n_inputs];
+    }
+  }
+  float* tout = temps + S.temp_off;
+  const int out_size = S.out_size;
   float mx = LOG ? NEG_INF : 0.0f;
   int o = lane;
-  // two output cells per lane and iteration: their loads are independent, which doubles the memory-level parallelism
-  for (; o + 32 < out_size; o += 64) {
-    const float *p0[NIN], *p1[NIN];
+  if constexpr (NIN * SC <= 12) {
+    // two cells per lane and iteration: both cells' loads are issued before either result is stored
+    for (; o + 32 < out_size; o += 64) {
+      float x0[NIN][SC], x1[NIN][SC];
 #pragma unroll
-    for (int k = 0; k < NIN; ++k) { p0[k] = src[k] + offs[k * out_size + o]; p1[k] = src[k] + offs[k * out_size + o + 32]; }
-    float a0 = LOG ? NEG_INF : 0.0f, a1 = a0;
-#pragma unroll 2
-    for (int sv = 0; sv < sum_card; ++sv) {
-      float q0 = *p0[0], q1 = *p1[0];
-      p0[0] += sb[0]; p1[0] += sb[0];
-#pragma unroll
-      for (int k = 1; k < NIN; ++k) {
-        const float x0 = *p0[k], x1 = *p1[k];
-        p0[k] += sb[k]; p1[k] += sb[k];
-        q0 = LOG ? q0 + x0 : q0 * x0;
-        q1 = LOG ? q1 + x1 : q1 * x1;
+      for (int k = 0; k < NIN; ++k) {
+        load_run<SC>(src[k] + offs[k * out_size + o], x0[k]);
+        load_run<SC>(src[k] + offs[k * out_size + o + 32], x1[k]);
       }
-      a0 = LOG ? lse2<LOG>(a0, q0) : a0 + q0;
-      a1 = LOG ? lse2<LOG>(a1, q1) : a1 + q1;
+      const float a0 = cell_value<LOG, NIN, SC>(x0, scale), a1 = cell_value<LOG, NIN, SC>(x1, scale);
+      tout[o] = a0; tout[o + 32] = a1;
+      mx = fmaxf(mx, fmaxf(a0, a1));
     }
-    tout[o] = a0; tout[o + 32] = a1;
-    mx = fmaxf(mx, fmaxf(a0, a1));
   }
   for (; o < out_size; o += 32) {
-    const float* p[NIN];
+    float x[NIN][SC];
 #pragma unroll
-    for (int k = 0; k < NIN; ++k) p[k] = src[k] + offs[k * out_size + o];
+    for (int k = 0; k < NIN; ++k) load_run<SC>(src[k] + offs[k * out_size + o], x[k]);
+    const float a = cell_value<LOG, NIN, SC>(x, scale);
+    tout[o] = a;
+    mx = fmaxf(mx, a);
+  }
+  return mx;
+}
+
+// strided steps: any sum stride, any cardinality, up to CBN_MAX_CONTRACT_INPUTS factors.  Every temporary is scaled as it
+// is read (with up to 16 factors the product of the scales alone could leave the fp32 range).
+template <bool LOG>
+__device__ __noinline__ float row_step_strided(const RowStepDev& S, const int* __restrict__ offs, const RowInputDev* __restrict__ sin,
+                                               const RowStepDev* __restrict__ sst, int n_inputs, const int* __restrict__ base,
+                                               float* temps, const float* __restrict__ tscale, int lane) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  float* tout = temps + S.temp_off;
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = lane; o < S.out_size; o += 32) {
     float acc = LOG ? NEG_INF : 0.0f;
-#pragma unroll 4
-    for (int sv = 0; sv < sum_card; ++sv) {
-      float prod = *p[0];
-      p[0] += sb[0];
-#pragma unroll
-      for (int k = 1; k < NIN; ++k) {
-        const float x = *p[k];
-        p[k] += sb[k];
-        prod = LOG ? prod + x : prod * x;
+    for (int sv = 0; sv < S.sum_card; ++sv) {
+      float prod = LOG ? 0.0f : 1.0f;
+      for (int k = 0; k < S.n_in; ++k) {
+        const int id = S.in_id[k];
+        const float* src = id < n_inputs ? sin[id].data + base[id] : temps + sst[id - n_inputs].temp_off;
+        const float sk = id < n_inputs ? (LOG ? 0.0f : 1.0f) : tscale[id - n_inputs];
+        const float x = src[offs[k * S.out_size + o] + sv * S.sum_stride[k]];
+        prod = LOG ? prod + (x + sk) : prod * (x * sk);
       }
       acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
     }
@@ -1427,26 +1506,26 @@ __device__ __forceinline__ float row_step_body(const RowStepDev& S, const int* _
   return mx;
 }
 
-template <bool LOG>
-__device__ __noinline__ float row_step_generic(const RowStepDev& S, const int* __restrict__ offs, const float* const* srcs, float* __restrict__ tout,
-                                               int lane) {
-  const float NEG_INF = __int_as_float(0xff800000);
-  float mx = LOG ? NEG_INF : 0.0f;
-  for (int o = lane; o < S.out_size; o += 32) {
-    float acc = LOG ? NEG_INF : 0.0f;
-    for (int sv = 0; sv < S.sum_card; ++sv) {
-      float prod = LOG ? 0.0f : 1.0f;
-      for (int k = 0; k < S.n_in; ++k) {
-        const float x = srcs[k][offs[k * S.out_size + o] + sv * S.sum_stride[k]];
-        prod = LOG ? prod + x : prod * x;
-      }
-      acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
-    }
-    tout[o] = acc;
-    mx = fmaxf(mx, acc);
+template <bool LOG, int NIN>
+__device__ __forceinline__ float row_step_unit_nin(const RowStepDev& S, const int* __restrict__ offs, const RowInputDev* __restrict__ sin,
+                                                   const RowStepDev* __restrict__ sst, int n_inputs, const int* __restrict__ base,
+                                                   float* temps, const float* __restrict__ tscale, int lane) {
+  switch (S.sum_card) {
+    case 1: return row_step_unit<LOG, NIN, 1>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 2: return row_step_unit<LOG, NIN, 2>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 3: return row_step_unit<LOG, NIN, 3>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 4: return row_step_unit<LOG, NIN, 4>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 5: return row_step_unit<LOG, NIN, 5>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 6: return row_step_unit<LOG, NIN, 6>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    case 7: return row_step_unit<LOG, NIN, 7>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
+    default: return row_step_unit<LOG, NIN, 8>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
   }
-  return mx;
 }
+
+// bytes of the per-warp region in front of the temporaries: evidence codes, slice offsets of the static inputs, step scales
+__host__ __device__ inline int rows_code_words(int n_evidence) { return (((n_evidence + 3) >> 2) + 3) & ~3; }
+__host__ __device__ inline int rows_base_words(int n_inputs) { return (n_inputs + 3) & ~3; }
+__host__ __device__ inline int rows_scale_words(int n_steps) { return (n_steps + 3) & ~3; }
 
 template <bool LOG>
 __global__ void __launch_bounds__(ROWS_TPB, 4) ve_rows_kernel(const RowInputDev* __restrict__ inputs, int n_inputs,
@@ -1465,12 +1544,13 @@ __global__ void __launch_bounds__(ROWS_TPB, 4) ve_rows_kernel(const RowInputDev*
   for (int i = threadIdx.x; i < off_ints; i += blockDim.x) soff[i] = off_pool[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int code_words = (n_evidence + 3) >> 2, base_words = (n_inputs + 3) & ~3;
-  const int per_warp = ((code_words + 3) & ~3) + base_words + temp_floats;
+  const int code_words = rows_code_words(n_evidence), base_words = rows_base_words(n_inputs), scale_words = rows_scale_words(n_steps);
+  const int per_warp = code_words + base_words + scale_words + temp_floats;
   int* wmem = soff + ((off_ints + 3) & ~3) + size_t(warp) * per_warp;
   uint8_t* codes = reinterpret_cast<uint8_t*>(wmem);
-  int* base = wmem + ((code_words + 3) & ~3);
-  float* temps = reinterpret_cast<float*>(base + base_words);
+  int* base = wmem + code_words;
+  float* tscale = reinterpret_cast<float*>(base + base_words);
+  float* temps = tscale + scale_words;
   const float NEG_INF = __int_as_float(0xff800000);
   for (int64_t row = int64_t(blockIdx.x) * ROWS_WARPS + warp; row < n_rows; row += int64_t(gridDim.x) * ROWS_WARPS) {
     // the row's evidence codes (one byte per evidence column), then the slice offset of every static input
@@ -1492,37 +1572,31 @@ __global__ void __launch_bounds__(ROWS_TPB, 4) ve_rows_kernel(const RowInputDev*
     if (!bad) {
       for (int j = 0; j < n_steps; ++j) {
         const RowStepDev& S = sst[j];
-        float* tout = temps + S.temp_off;
         const int* offs = soff + S.off_at;
-        const float* srcs[CBN_MAX_CONTRACT_INPUTS];
-#pragma unroll
-        for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
-          if (k < S.n_in) {
-            const int id = S.in_id[k];
-            srcs[k] = id < n_inputs ? sin[id].data + base[id] : temps + sst[id - n_inputs].temp_off;
-          }
         float mx;
-        switch (S.n_in) {
-          case 1: mx = row_step_body<LOG, 1>(S, offs, srcs, tout, lane); break;
-          case 2: mx = row_step_body<LOG, 2>(S, offs, srcs, tout, lane); break;
-          case 3: mx = row_step_body<LOG, 3>(S, offs, srcs, tout, lane); break;
-          case 4: mx = row_step_body<LOG, 4>(S, offs, srcs, tout, lane); break;
-          default: mx = row_step_generic<LOG>(S, offs, srcs, tout, lane); break;
+        if (S.unit) {
+          switch (S.n_in) {
+            case 1: mx = row_step_unit_nin<LOG, 1>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane); break;
+            case 2: mx = row_step_unit_nin<LOG, 2>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane); break;
+            case 3: mx = row_step_unit_nin<LOG, 3>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane); break;
+            default: mx = row_step_unit_nin<LOG, 4>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane); break;
+          }
+        } else {
+          mx = row_step_strided<LOG>(S, offs, sin, sst, n_inputs, base, temps, tscale, lane);
         }
         mx = warp_max(mx);
-        __syncwarp();
-        if (j + 1 < n_steps) {
-          // keep the temporary in range: divide by its maximum (subtract it in log space)
-          const int n_out = S.out_size;      // a register copy: the stores below could alias the descriptor in shared memory
-          float* __restrict__ tp = tout + lane;
-          if (LOG) {
-            if (mx != NEG_INF) for (int o = lane; o < n_out; o += 32, tp += 32) *tp -= mx;
-          } else if (mx > 0.0f) {
-            const float inv = 1.0f / mx;
-            for (int o = lane; o < n_out; o += 32, tp += 32) *tp *= inv;
-          }
-          __syncwarp();
+        // the scale the consuming step applies (same value in every lane).  The unrolled bodies apply the product of their
+        // (at most 4) temporaries' scales to the finished cell: a scale far from 1 would push the unscaled product out of
+        // range first, so such a temporary is rescaled in place right here (rare; every lane rescales the cells it wrote)
+        float sc = LOG ? (mx == NEG_INF ? 0.0f : -mx) : (mx > 0.0f ? 1.0f / mx : 1.0f);
+        if (!LOG && (sc > 4096.0f || sc < 1.0f / 4096.0f)) {
+          float* tout = temps + S.temp_off;
+          const int n = S.out_size;
+          for (int o = lane; o < n; o += 32) tout[o] *= sc;
+          sc = 1.0f;
         }
+        if (lane == 0) tscale[j] = sc;
+        __syncwarp();          // this step's stores and its scale become visible to the other lanes
       }
     }
     // normalise the last temporary over the target and write the posterior row
@@ -1688,6 +1762,13 @@ __global__ void __launch_bounds__(ROWT_TPB) ve_rows_thread_kernel(const RowInput
 }
 }  // namespace
 
+// CBN_ROWS_UNIT=0 sends every step through the strided bodies (testing / comparison)
+static int rows_unit_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("CBN_ROWS_UNIT"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
 extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                                        const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps,
                                        int32_t n_steps, int32_t flags, cbn_stream stream, cbn_ve_plan** out) {
@@ -1698,6 +1779,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: bad argument");
   DeviceGuard g(ctx->device);
   std::vector<RowInputDev> hi(n_inputs);
+  std::vector<long long> reach_of(n_inputs, 0);       // largest slice offset the evidence codes can produce
   for (int k = 0; k < n_inputs; ++k) {
     const cbn_row_input& I = inputs[k];
     if (!I.data || I.n_ev < 0 || I.n_ev > GATHER_MAX_TABLE_EV || I.n_cells < 1 || I.n_cells > 0x7fffffffll)
@@ -1714,6 +1796,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
       reach += (long long)(ev_cards[I.ev_slot[j]] - 1) * I.ev_stride[j];
     }
     if (reach >= I.n_cells) return cbn_fail(ctx, CBN_ERR_INVALID, "row input %d: evidence strides leave the table", k);
+    reach_of[k] = reach;
   }
   std::vector<RowStepDev> hs(n_steps);
   int temp = 0;
@@ -1723,23 +1806,46 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
     if (S.out_size < 1 || S.sum_card < 1 || S.n_in < 1 || S.n_in > CBN_MAX_CONTRACT_INPUTS || !S.offsets)
       return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: bad descriptor", j);
     hs[j] = RowStepDev{};
-    hs[j].offsets = S.offsets; hs[j].out_size = S.out_size; hs[j].sum_card = S.sum_card; hs[j].n_in = S.n_in;
+    hs[j].offsets = nullptr; hs[j].out_size = S.out_size; hs[j].sum_card = S.sum_card; hs[j].n_in = S.n_in;
     hs[j].temp_off = temp;
     hs[j].off_at = (int)off_ints;
+    // the unrolled bodies need the summed variable innermost in every factor, and runs aligned for their vector loads
+    const int vec = S.sum_card % 4 == 0 ? 4 : S.sum_card % 2 == 0 ? 2 : 1;
+    bool unit = S.n_in <= ROWS_UNIT_MAX_IN && S.sum_card <= ROWS_UNIT_MAX_CARD;
     for (int k = 0; k < S.n_in; ++k) {
       if (S.in_id[k] < 0 || S.in_id[k] >= n_inputs + j)
         return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: input %d refers to a later step", j, k);
       hs[j].in_id[k] = S.in_id[k];
       hs[j].sum_stride[k] = S.sum_stride[k];
+      unit = unit && (S.sum_card == 1 || S.sum_stride[k] == 1);
+      if (unit && vec > 1) {
+        if (S.in_id[k] < n_inputs) {
+          const RowInputDev& I = hi[S.in_id[k]];
+          unit = unit && (reinterpret_cast<uintptr_t>(I.data) % (4 * vec) == 0);
+          for (int a = 0; a < I.n_ev; ++a) unit = unit && (I.stride[a] % vec == 0);
+        }
+        const int32_t* o = S.offsets + size_t(k) * S.out_size;
+        for (int c = 0; unit && c < S.out_size; ++c) unit = (o[c] % vec == 0);
+      }
+      // every read stays inside its factor
+      const int32_t* o = S.offsets + size_t(k) * S.out_size;
+      const long long span = (long long)(S.sum_card - 1) * S.sum_stride[k];
+      const long long cells = S.in_id[k] < n_inputs ? (long long)hi[S.in_id[k]].n_cells - reach_of[S.in_id[k]]
+                                                     : (long long)steps[S.in_id[k] - n_inputs].out_size;
+      if (S.sum_stride[k] < 0) return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: negative sum stride", j);
+      for (int c = 0; c < S.out_size; ++c)
+        if (o[c] < 0 || o[c] + span >= cells)
+          return cbn_fail(ctx, CBN_ERR_INVALID, "row step %d: offset %d of input %d leaves the factor", j, c, k);
     }
+    if (rows_unit_mode() == 0) unit = false;
+    hs[j].unit = unit ? 1 : 0;
     temp += (S.out_size + 3) & ~3;
     off_ints += (long long)S.n_in * S.out_size;
     terms += (long long)S.n_in * S.out_size * S.sum_card;
   }
   if (steps[n_steps - 1].out_size != card_t)
     return cbn_fail(ctx, CBN_ERR_INVALID, "cbn_ve_plan_create_rows: the last step must produce card_t cells");
-  const size_t code_words = ((size_t(n_evidence) + 3) / 4 + 3) & ~size_t(3);
-  const size_t per_warp = code_words + ((n_inputs + 3) & ~3) + temp;
+  const size_t per_warp = size_t(rows_code_words(n_evidence)) + rows_base_words(n_inputs) + rows_scale_words(n_steps) + temp;
   const size_t smem = size_t(n_steps) * sizeof(RowStepDev) + size_t(n_inputs) * sizeof(RowInputDev) +
                       size_t((off_ints + 3) & ~3ll) * 4 + size_t(ROWS_WARPS) * per_warp * 4;
   if (smem > 200 * 1024)
@@ -1766,7 +1872,7 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
   if (e == cudaSuccess) e = cudaMalloc(&p->d_row_offsets, size_t(std::max<long long>(off_ints, 1)) * 4);
   for (int j = 0; e == cudaSuccess && j < n_steps; ++j)
     e = cudaMemcpyAsync((int*)p->d_row_offsets + hs[j].off_at, steps[j].offsets, size_t(steps[j].n_in) * steps[j].out_size * 4,
-                        cudaMemcpyDeviceToDevice, cs);
+                        cudaMemcpyHostToDevice, cs);
   if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ve_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

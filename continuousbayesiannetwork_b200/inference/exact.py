@@ -24,7 +24,7 @@ class ExactInference(BaseInference):
             raise ValueError(f"normalization must be 'row' or 'global_max', got {self.normalization!r}")
         self._budget = {k: int(config[k]) for k in ("table_budget_cells", "merge_budget_cells", "row_temp_floats")
                         if config and k in config}
-        for k in ("log_space", "rescale", "profile_compile"):
+        for k in ("log_space", "rescale", "profile_compile", "row_unit_layout"):
             if config and k in config:
                 self._budget[k] = bool(config[k])
 

@@ -259,7 +259,7 @@ class RowPlan:
     compile time + a per-row schedule of product / sum-out steps (``cbn_ve_plan_create_rows``)."""
 
     def __init__(self, tables_owner, target: int, evidence: List[int], card_t: int, inputs: List[Factor],
-                 steps: List[dict], offsets: torch.Tensor, stats: PlanStats, log_space: bool):
+                 steps: List[dict], offsets, stats: PlanStats, log_space: bool):
         self.owner = tables_owner
         self.ctx = tables_owner.ctx
         self.device = tables_owner.device
@@ -267,7 +267,7 @@ class RowPlan:
         self.evidence = list(evidence)
         self.card_t = card_t
         self.inputs = inputs            # keep the tables alive
-        self.offsets = offsets
+        self.offsets = offsets          # host int32 array (numpy): copied into the plan at creation
         self.stats = stats
         self.log_space = log_space
         self.handle = None
@@ -296,7 +296,7 @@ class RowPlan:
             for k, (i, ss) in enumerate(zip(st["in_id"], st["sum_stride"])):
                 sts[j].in_id[k] = i
                 sts[j].sum_stride[k] = ss
-            sts[j].offsets = offsets.data_ptr() + 4 * st["offsets_at"]
+            sts[j].offsets = offsets.ctypes.data + 4 * st["offsets_at"]
         ev_cards = (C.c_int32 * max(len(self.evidence), 1))(*[cards[v] for v in self.evidence])
         h = C.c_void_p()
         N.check(N.lib().cbn_ve_plan_create_rows(self.ctx.handle, len(self.evidence), ev_cards, card_t, ins, len(inputs), sts,
@@ -402,7 +402,7 @@ class VECompiler:
 
     def __init__(self, tables, table_budget_cells: int = 1 << 28, merge_budget_cells: int = 1 << 24,
                  check_support: bool = True, row_temp_floats: int = 5000, log_space: bool = False, rescale: bool = True,
-                 profile_compile: bool = False):
+                 profile_compile: bool = False, row_unit_layout: bool = True):
         self.t = tables
         # range control of the compile-time elimination: after every contraction each evidence slice of the result is
         # divided by its maximum (cbn_factor_rescale) -- a factor of the evidence configuration only, which cancels in the
@@ -415,6 +415,7 @@ class VECompiler:
         self.merge_budget = int(merge_budget_cells)
         self.check_support = check_support
         self.row_temp_floats = int(row_temp_floats)     # per-row temporaries of the per-row executor (shared memory)
+        self.row_unit_layout = bool(row_unit_layout)    # lay every per-row factor out with its consumer's summed variable innermost
         self.log_space = bool(log_space)
         self._cache: Dict[tuple, QueryPlan] = {}
         self._has_zero: Dict[int, bool] = {}
@@ -692,12 +693,70 @@ class VECompiler:
     # ---------------------------------------------------------------- per-row schedule
     def _row_plan(self, T: int, E: List[int], statics: List[Factor], hidden: List[int], stats: PlanStats, dry: bool):
         """Schedule the elimination of ``hidden`` per row: evidence axes of the static tables are sliced by the
-        row's codes, so only hidden axes (and the target) count towards the size of a temporary."""
+        row's codes, so only hidden axes (and the target) count towards the size of a temporary.
+
+        Two passes.  The first fixes the elimination order and which factors meet in which step; the second chooses the
+        LAYOUT of every factor.  A factor -- static table or temporary -- is consumed by exactly one step, so it is laid
+        out for that step: the variable the step sums over innermost (stride 1), which is what the executor's unrolled
+        step bodies need (csrc/ve.cu, ``row_step_unit``).  Static tables whose axes are in a different order are
+        permuted once, here, at compile time."""
         import numpy as np
 
         cards = self.t.cards
         Eset = set(E)
         n_in = len(statics)
+        MAXIN = N.MAX_CONTRACT_INPUTS
+
+        def size_of(scope):
+            return _prod(cards[v] for v in scope)
+
+        # pass 1: (input keys, output key, output scope, summed variable or None)
+        live = {k: [v for v in f.scope if v not in Eset] for k, f in enumerate(statics)}
+        ops = []
+        next_key = n_in
+        g = _Greedy(cards, {k: list(sc) for k, sc in live.items()}, hidden)
+        while g.hidden:
+            v, _, sc = g.best()
+            keys = list(g.touching(v))
+            while len(keys) > MAXIN:                           # pre-multiply the two smallest
+                order = sorted(range(len(keys)), key=lambda i: size_of(live[keys[i]]))
+                ka, kb = keys[order[0]], keys[order[1]]
+                psc = sorted(set(live[ka]) | set(live[kb]))
+                ops.append(([ka, kb], next_key, psc, None))
+                g.replace([ka, kb], next_key, psc)
+                del live[ka], live[kb]
+                live[next_key] = psc
+                keys = [k for k in keys if k not in (ka, kb)] + [next_key]
+                next_key += 1
+            out_scope = sorted(sc)
+            ops.append((keys, next_key, out_scope, v))
+            for k in keys:
+                del live[k]
+            live[next_key] = out_scope
+            g.eliminate(v, next_key, out_scope)
+            next_key += 1
+            stats.n_steps += 1
+        rest = list(live.keys())
+        # final product over what is left (free scope is empty or [T])
+        while len(rest) > MAXIN:
+            ops.append((rest[:MAXIN], next_key, [T], None))
+            rest = rest[MAXIN:] + [next_key]
+            next_key += 1
+        ops.append((rest, next_key, [T], None))
+
+        # pass 2: layouts, offset tables, temporaries
+        inner = {}                                             # factor key -> the variable its consumer sums over
+        for keys, _, _, v in ops:
+            for k in keys:
+                inner[k] = v
+
+        def lay_out(scope, key):
+            v = inner.get(key) if self.row_unit_layout else None
+            sc = sorted(scope, key=lambda a: (a == T, a))
+            if v is not None and v in sc:
+                sc.remove(v)
+                sc.append(v)
+            return sc
 
         def strides_of(scope):
             st, s = {}, 1
@@ -706,20 +765,28 @@ class VECompiler:
                 s *= cards[v]
             return st
 
-        # row factors: (id, free scope, strides over the free axes)
-        rf = []
+        laid = []                                              # the static tables as the executor reads them
+        fac = {}                                               # key -> (input id, free scope, strides over the free axes)
         for k, f in enumerate(statics):
-            st = strides_of(f.scope)
             free = [v for v in f.scope if v not in Eset]
-            rf.append((k, free, {v: st[v] for v in free}))
+            want = [v for v in f.scope if v in Eset] + lay_out(free, k) if self.row_unit_layout else list(f.scope)
+            if want != list(f.scope):
+                perm = [f.scope.index(v) for v in want]
+                tensor = None
+                if f.tensor is not None:
+                    tensor = f.tensor.reshape([cards[v] for v in f.scope]).permute(perm).contiguous().reshape(-1)
+                f = Factor(want, tensor)
+            elif f.tensor is not None and f.tensor.data_ptr() % 16:
+                f = Factor(list(f.scope), f.tensor.clone())    # a view into a packed buffer: realign for vector loads
+            laid.append(f)
+            st = strides_of(f.scope)
+            fac[k] = (k, [v for v in f.scope if v not in Eset], {v: st[v] for v in f.scope if v not in Eset})
         steps, off_chunks, off_at, temp_total = [], [], 0, 0
-
-        def emit(inputs, out_scope, sum_var):
-            nonlocal off_at, temp_total
+        for keys, out_key, out_scope, sum_var in ops:
+            inputs = [fac[k] for k in keys]
+            out_scope = lay_out(out_scope, out_key)
             out_shape = [cards[v] for v in out_scope]
-            out_size = 1
-            for c in out_shape:
-                out_size *= c
+            out_size = _prod(out_shape)
             if temp_total + (out_size + 3) // 4 * 4 > self.row_temp_floats:
                 raise PlanTooLarge(
                     f"per-row elimination needs more than {temp_total + out_size} floats of temporaries per row "
@@ -731,64 +798,25 @@ class VECompiler:
                 for d, v in enumerate(out_scope):
                     if v in st:
                         offs[k] += grids[d] * st[v]
-            steps.append({"out_size": out_size, "sum_card": cards[sum_var] if sum_var is not None else 1,
-                          "in_id": [i for i, _, _ in inputs],
+            sum_card = cards[sum_var] if sum_var is not None else 1
+            steps.append({"out_size": out_size, "sum_card": sum_card, "in_id": [i for i, _, _ in inputs],
                           "sum_stride": [st.get(sum_var, 0) if sum_var is not None else 0 for _, _, st in inputs],
                           "offsets_at": off_at})
             off_chunks.append(offs.astype(np.int32).reshape(-1))
             off_at += offs.size
             temp_total += (out_size + 3) // 4 * 4
-            stats.contraction_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
-            stats.per_row_madds += out_size * (cards[sum_var] if sum_var is not None else 1) * len(inputs)
-            return (n_in + len(steps) - 1, list(out_scope), strides_of(out_scope))
-
-        def size_of(scope):
-            s = 1
-            for v in scope:
-                s *= cards[v]
-            return s
-
-        live = dict(enumerate(rf))                      # key -> (input id, free scope, strides)
-        next_key = len(rf)
-        g = _Greedy(cards, {k: f[1] for k, f in live.items()}, hidden)
-        while g.hidden:
-            v, _, sc = g.best()
-            keys = g.touching(v)
-            touching = [live[k] for k in keys]
-            out_scope = sorted(sc, key=lambda a: (a == T, a))
-            while len(touching) > N.MAX_CONTRACT_INPUTS:       # pre-multiply the two smallest
-                order = sorted(range(len(touching)), key=lambda i: size_of(touching[i][1]))
-                ia, ib = order[0], order[1]
-                a, b = touching[ia], touching[ib]
-                psc = sorted(set(a[1]) | set(b[1]), key=lambda x: (x == T, x))
-                prod = emit([a, b], psc, None)
-                g.replace([keys[ia], keys[ib]], next_key, psc)
-                for k in (keys[ia], keys[ib]):
-                    del live[k]
-                live[next_key] = prod
-                keys = [k for i, k in enumerate(keys) if i not in (ia, ib)] + [next_key]
-                touching = [f for i, f in enumerate(touching) if i not in (ia, ib)] + [prod]
-                next_key += 1
-            res = emit(touching, out_scope, v)
-            for k in keys:
-                del live[k]
-            live[next_key] = res
-            g.eliminate(v, next_key, out_scope)
-            next_key += 1
-            stats.n_steps += 1
-        rf = list(live.values())
-        # final product over what is left (free scope is empty or [T])
-        while len(rf) > N.MAX_CONTRACT_INPUTS:
-            rf = rf[N.MAX_CONTRACT_INPUTS:] + [emit(rf[:N.MAX_CONTRACT_INPUTS], [T], None)]
-        emit(rf, [T], None)
+            stats.contraction_madds += out_size * sum_card * len(inputs)
+            stats.per_row_madds += out_size * sum_card * len(inputs)
+            fac[out_key] = (n_in + len(steps) - 1, list(out_scope), strides_of(out_scope))
+        offsets = np.ascontiguousarray(np.concatenate(off_chunks), dtype=np.int32)
         # the schedule as plain host data (what cbn_ve_plan_create_rows receives): kept for inspection and for the
         # CPU-side interpreter of tests/test_host_logic.py
-        self.last_row_schedule = {"target": T, "evidence": list(E), "static_scopes": [list(f.scope) for f in statics],
-                                  "steps": steps, "offsets": np.concatenate(off_chunks)}
+        self.last_row_schedule = {"target": T, "evidence": list(E), "static_scopes": [list(f.scope) for f in laid],
+                                  "static_source_scopes": [list(f.scope) for f in statics],
+                                  "steps": steps, "offsets": offsets}
         if dry:
             return None
-        offsets = torch.from_numpy(np.concatenate(off_chunks)).to(self.t.device)
-        return RowPlan(self.t, T, E, cards[T], statics, steps, offsets, stats, self.log_space)
+        return RowPlan(self.t, T, E, cards[T], laid, steps, offsets, stats, self.log_space)
 
     def _merge_finals(self, finals: List[Factor], sort_scope, stats: PlanStats, dry: bool, T: int) -> List[Factor]:
         """Multiply final tables together while the product stays within the merge budget: fewer gathers

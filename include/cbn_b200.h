@@ -253,7 +253,11 @@ CBN_API int cbn_ve_plan_outputs(const cbn_ve_plan* plan);
  * intermediates live in shared memory (one warp per row).  Step j produces a temporary of out_size cells:
  *     tmp_j[o] = sum_{s < sum_card} prod_k in_k[ offsets[k][o] + s * sum_stride[k] ]
  * where in_k is a static input (sliced by the row's evidence codes) or an earlier temporary; the last step has
- * out_size == card_t and is normalised over the target.  flags bit 0: run in log space (log-sum-exp). */
+ * out_size == card_t and is normalised over the target.  flags bit 0: run in log space (log-sum-exp).
+ * Every factor is consumed by exactly one step, so a caller is free to lay it out for that step: with the summed
+ * variable innermost (sum_stride[k] == 1 for every k, sum_card <= 8, at most 4 factors, 16-byte aligned tables) the
+ * step runs on bodies that read each cell's terms as one 64/128-bit run; any other strides are accepted and run on
+ * the strided bodies. */
 #define CBN_ROWS_LOG_SPACE 1
 typedef struct cbn_row_input {
   const float* data; /* device */
@@ -268,7 +272,7 @@ typedef struct cbn_row_step {
   int32_t n_in;
   int32_t in_id[CBN_MAX_CONTRACT_INPUTS];      /* < n_inputs: static input, else temporary of step in_id - n_inputs */
   int32_t sum_stride[CBN_MAX_CONTRACT_INPUTS];
-  const int32_t* offsets;                      /* device int32 [n_in][out_size] */
+  const int32_t* offsets;                      /* HOST int32 [n_in][out_size]; copied (and range-checked) at plan creation */
 } cbn_row_step;
 CBN_API int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const int32_t* ev_cards, int32_t card_t,
                             const cbn_row_input* inputs, int32_t n_inputs, const cbn_row_step* steps, int32_t n_steps,

@@ -173,10 +173,18 @@ def test_row_schedule_interpreted_on_the_cpu_matches_the_oracle():
         ev_ids = sch["evidence"]
         assert ev_ids == [spec.names.index(e) for e in ev_names]
         statics = []
-        for scope in sch["static_scopes"]:               # with a budget of 1 the static tables are the CPTs themselves
-            node = scope[-1]
-            assert scope == spec.parents[node] + [node]
-            statics.append((scope, np.asarray(spec.cpts[node], dtype=np.float64).reshape(-1)))
+        n_permuted = 0
+        for scope, source in zip(sch["static_scopes"], sch["static_source_scopes"]):
+            # with a budget of 1 the static tables are the CPTs themselves, each laid out for the step that consumes it
+            # (evidence axes first, the variable that step sums over innermost)
+            node = source[-1]
+            assert source == spec.parents[node] + [node] and sorted(scope) == sorted(source)
+            cpt = np.asarray(spec.cpts[node], dtype=np.float64).reshape([spec.cards[v] for v in source])
+            statics.append((scope, np.ascontiguousarray(cpt.transpose([source.index(v) for v in scope])).reshape(-1)))
+            n_permuted += scope != source
+        assert n_permuted > 0
+        for st in sch["steps"]:                          # the layout contract of the executor's unrolled step bodies
+            assert st["sum_card"] == 1 or all(s == 1 for s in st["sum_stride"])
         codes = synth.sample_forward_numpy(spec, 9, 0, 40)
         rows = codes[ev_ids].T
         got = np.zeros((rows.shape[0], spec.cards[sch["target"]]))

@@ -662,13 +662,17 @@ def test_per_row_executor_matches_oracle():
     ev = codes[ids].T.copy()
     ev[5, 3] = 255                                              # unseen value -> zero row
     net = _net(spec)
-    for log_space in (False, True):
+    # unit = the planner lays every factor out for the step that consumes it (the executor's unrolled step bodies);
+    # without it the schedule keeps the tables' own axis order and runs on the strided bodies
+    for log_space, unit in ((False, True), (True, True), (False, False), (True, False)):
         t = tables_from_spec(spec, DEV)
         t.set_cond_tables(spec.cpts)
-        infer = bind_inference(t, table_budget_cells=1 << 10, log_space=log_space)
+        infer = bind_inference(t, table_budget_cells=1 << 10, log_space=log_space, row_unit_layout=unit)
         for target in ("HYPOVOLEMIA", "VENTLUNG", "CATECHOL"):
             plan = infer.plan(target, synth.ALARM_EVIDENCE)
             assert isinstance(plan, RowPlan) and plan.stats.per_row_hidden > 0
+            sums = [st for st in infer.compiler.last_row_schedule["steps"] if st["sum_card"] > 1]
+            assert all(s == 1 for st in sums for s in st["sum_stride"]) == unit
             got = plan.run_codes(_codes_matrix(ev), ev.shape[0]).cpu().numpy()
             ok = np.ones(ev.shape[0], bool); ok[5] = False
             want = O.ve_posterior(net, spec.names.index(target), ids, ev[ok], dtype=torch.float64)
