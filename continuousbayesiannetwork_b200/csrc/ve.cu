@@ -1631,8 +1631,8 @@ __global__ void __launch_bounds__(ROWS_TPB, 4) ve_rows_kernel(const RowInputDev*
 // gathered through L1 (the tables of such plans are small), and a step's offsets are shared-memory broadcasts.
 namespace {
 constexpr int ROWT_TPB = 128;
-constexpr int ROWT_MAX_TEMPS = 64;
-constexpr int ROWT_MAX_TERMS = 320;
+constexpr int ROWT_MAX_TEMPS = 96;
+constexpr int ROWT_MAX_TERMS = 480;
 
 template <bool LOG, int NIN>
 __device__ __forceinline__ float rowt_step(const RowStepDev& S, const int* __restrict__ offs, const float* const* gsrc, const int* tsrc,
@@ -1654,6 +1654,112 @@ __device__ __forceinline__ float rowt_step(const RowStepDev& S, const int* __res
 #pragma unroll
       for (int k = 0; k < NIN; ++k) {
         const int idx = off[k] + sv * ss[k];
+        const float x = t[k] < 0 ? __ldg(g[k] + idx) : tsm[(t[k] + idx) * ROWT_TPB + tid];
+        prod = LOG ? prod + x : prod * x;
+      }
+      acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
+    }
+    tsm[(S.temp_off + o) * ROWT_TPB + tid] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  return mx;
+}
+
+// unit-stride steps (RowStepDev::unit): the terms of a cell are one contiguous run of every factor -- one 64/128-bit
+// gather per static factor and cell instead of SC scalar ones
+template <bool LOG, int NIN, int SC>
+__device__ __forceinline__ float rowt_step_unit(const RowStepDev& S, const int* __restrict__ offs, const float* const (&g)[NIN],
+                                                const int (&t)[NIN], float* __restrict__ tsm, int tid) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const int out_size = S.out_size;
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = 0; o < out_size; ++o) {
+    float x[NIN][SC];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+      const int off = offs[k * out_size + o];
+      if (t[k] < 0) {
+        load_run<SC>(g[k] + off, x[k]);
+      } else {
+#pragma unroll
+        for (int sv = 0; sv < SC; ++sv) x[k][sv] = tsm[(t[k] + off + sv) * ROWT_TPB + tid];
+      }
+    }
+    const float acc = cell_value<LOG, NIN, SC>(x, LOG ? 0.0f : 1.0f);
+    tsm[(S.temp_off + o) * ROWT_TPB + tid] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  return mx;
+}
+
+// slice offset of a static table for this thread's row (coalesced code reads: consecutive threads = consecutive rows)
+__device__ __forceinline__ int rowt_base(const RowInputDev& I, const uint8_t* __restrict__ ev, int64_t ld, int64_t row, bool& bad) {
+  int b = 0;
+  for (int a = 0; a < I.n_ev; ++a) {
+    const int c = ev[int64_t(I.slot[a]) * ld + row];
+    bad |= (c >= I.card[a]);      // CBN_UNSEEN or any code outside the domain: the row is all zeros
+    b += c * I.stride[a];
+  }
+  return bad ? 0 : b;
+}
+
+template <bool LOG, int NIN>
+__device__ __forceinline__ float rowt_run_step(const RowStepDev& S, const int* __restrict__ offs, const RowInputDev* __restrict__ sin,
+                                               const RowStepDev* __restrict__ sst, int n_inputs, const uint8_t* __restrict__ ev,
+                                               int64_t ld, int64_t row, bool& bad, float* __restrict__ tsm, int tid) {
+  const float* g[NIN];
+  int t[NIN];
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) {
+    const int id = S.in_id[k];
+    if (id < n_inputs) {
+      g[k] = sin[id].data + rowt_base(sin[id], ev, ld, row, bad);
+      t[k] = -1;
+    } else {
+      g[k] = nullptr;
+      t[k] = sst[id - n_inputs].temp_off;
+    }
+  }
+  if (S.unit) {
+    switch (S.sum_card) {
+      case 1: return rowt_step_unit<LOG, NIN, 1>(S, offs, g, t, tsm, tid);
+      case 2: return rowt_step_unit<LOG, NIN, 2>(S, offs, g, t, tsm, tid);
+      case 3: return rowt_step_unit<LOG, NIN, 3>(S, offs, g, t, tsm, tid);
+      case 4: return rowt_step_unit<LOG, NIN, 4>(S, offs, g, t, tsm, tid);
+      case 5: return rowt_step_unit<LOG, NIN, 5>(S, offs, g, t, tsm, tid);
+      case 6: return rowt_step_unit<LOG, NIN, 6>(S, offs, g, t, tsm, tid);
+      case 7: return rowt_step_unit<LOG, NIN, 7>(S, offs, g, t, tsm, tid);
+      default: return rowt_step_unit<LOG, NIN, 8>(S, offs, g, t, tsm, tid);
+    }
+  }
+  return rowt_step<LOG, NIN>(S, offs, g, t, tsm, tid);
+}
+
+// more than four factors in one step (rare: a final product over many leftovers)
+template <bool LOG>
+__device__ __noinline__ float rowt_step_any(const RowStepDev& S, const int* __restrict__ offs, const RowInputDev* __restrict__ sin,
+                                            const RowStepDev* __restrict__ sst, int n_inputs, const uint8_t* __restrict__ ev,
+                                            int64_t ld, int64_t row, bool& bad, float* __restrict__ tsm, int tid) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float* g[CBN_MAX_CONTRACT_INPUTS];
+  int t[CBN_MAX_CONTRACT_INPUTS];
+  for (int k = 0; k < S.n_in; ++k) {
+    const int id = S.in_id[k];
+    if (id < n_inputs) {
+      g[k] = sin[id].data + rowt_base(sin[id], ev, ld, row, bad);
+      t[k] = -1;
+    } else {
+      g[k] = nullptr;
+      t[k] = sst[id - n_inputs].temp_off;
+    }
+  }
+  float mx = LOG ? NEG_INF : 0.0f;
+  for (int o = 0; o < S.out_size; ++o) {
+    float acc = LOG ? NEG_INF : 0.0f;
+    for (int sv = 0; sv < S.sum_card; ++sv) {
+      float prod = LOG ? 0.0f : 1.0f;
+      for (int k = 0; k < S.n_in; ++k) {
+        const int idx = offs[k * S.out_size + o] + sv * S.sum_stride[k];
         const float x = t[k] < 0 ? __ldg(g[k] + idx) : tsm[(t[k] + idx) * ROWT_TPB + tid];
         prod = LOG ? prod + x : prod * x;
       }
@@ -1689,51 +1795,14 @@ __global__ void __launch_bounds__(ROWT_TPB) ve_rows_thread_kernel(const RowInput
     bool bad = false;
     for (int j = 0; j < n_steps; ++j) {
       const RowStepDev& S = sst[j];
-      const float* gsrc[CBN_MAX_CONTRACT_INPUTS];
-      int tsrc[CBN_MAX_CONTRACT_INPUTS];
-#pragma unroll
-      for (int k = 0; k < CBN_MAX_CONTRACT_INPUTS; ++k)
-        if (k < S.n_in) {
-          const int id = S.in_id[k];
-          if (id < n_inputs) {                               // static table: slice it by this row's evidence codes
-            const RowInputDev& I = sin[id];
-            int b = 0;
-            for (int a = 0; a < I.n_ev; ++a) {
-              const int c = ev[int64_t(I.slot[a]) * ld + row];
-              bad |= (c >= I.card[a]);      // CBN_UNSEEN or any code outside the domain: the row is all zeros
-              b += c * I.stride[a];
-            }
-            gsrc[k] = I.data + (bad ? 0 : b);
-            tsrc[k] = -1;
-          } else {
-            gsrc[k] = nullptr;
-            tsrc[k] = sst[id - n_inputs].temp_off;
-          }
-        }
       const int* offs = soff + S.off_at;
       float mx;
       switch (S.n_in) {
-        case 1: mx = rowt_step<LOG, 1>(S, offs, gsrc, tsrc, tsm, tid); break;
-        case 2: mx = rowt_step<LOG, 2>(S, offs, gsrc, tsrc, tsm, tid); break;
-        case 3: mx = rowt_step<LOG, 3>(S, offs, gsrc, tsrc, tsm, tid); break;
-        case 4: mx = rowt_step<LOG, 4>(S, offs, gsrc, tsrc, tsm, tid); break;
-        default: {
-          mx = LOG ? NEG_INF : 0.0f;
-          for (int o = 0; o < S.out_size; ++o) {
-            float acc = LOG ? NEG_INF : 0.0f;
-            for (int sv = 0; sv < S.sum_card; ++sv) {
-              float prod = LOG ? 0.0f : 1.0f;
-              for (int k = 0; k < S.n_in; ++k) {
-                const int idx = offs[k * S.out_size + o] + sv * S.sum_stride[k];
-                const float x = tsrc[k] < 0 ? __ldg(gsrc[k] + idx) : tsm[(tsrc[k] + idx) * ROWT_TPB + tid];
-                prod = LOG ? prod + x : prod * x;
-              }
-              acc = LOG ? lse2<LOG>(acc, prod) : acc + prod;
-            }
-            tsm[(S.temp_off + o) * ROWT_TPB + tid] = acc;
-            mx = fmaxf(mx, acc);
-          }
-        }
+        case 1: mx = rowt_run_step<LOG, 1>(S, offs, sin, sst, n_inputs, ev, ld, row, bad, tsm, tid); break;
+        case 2: mx = rowt_run_step<LOG, 2>(S, offs, sin, sst, n_inputs, ev, ld, row, bad, tsm, tid); break;
+        case 3: mx = rowt_run_step<LOG, 3>(S, offs, sin, sst, n_inputs, ev, ld, row, bad, tsm, tid); break;
+        case 4: mx = rowt_run_step<LOG, 4>(S, offs, sin, sst, n_inputs, ev, ld, row, bad, tsm, tid); break;
+        default: mx = rowt_step_any<LOG>(S, offs, sin, sst, n_inputs, ev, ld, row, bad, tsm, tid); break;
       }
       if (j + 1 < n_steps) {       // keep the temporary in range (a per-row constant cancels in the final normalisation)
         if (LOG) {
@@ -1861,7 +1930,10 @@ extern "C" int cbn_ve_plan_create_rows(cbn_ctx* ctx, int32_t n_evidence, const i
                         size_t(temp) * ROWT_TPB * 4;
   // ... as long as the schedule is short: its table reads are per-thread gathers (one L1 sector each), which lose to the
   // warp-per-row kernel's coalesced slice reads beyond a few hundred terms per row (measured, tools/exp_rows.py)
-  p->rows_per_thread = temp <= ROWT_MAX_TEMPS && terms <= ROWT_MAX_TERMS && p->rows_thread_smem <= 100 * 1024;
+  static int max_temps = -1, max_terms = -1;
+  if (max_temps < 0) { const char* e = getenv("CBN_ROWT_MAX_TEMPS"); max_temps = e ? atoi(e) : ROWT_MAX_TEMPS; }
+  if (max_terms < 0) { const char* e = getenv("CBN_ROWT_MAX_TERMS"); max_terms = e ? atoi(e) : ROWT_MAX_TERMS; }
+  p->rows_per_thread = temp <= max_temps && terms <= max_terms && p->rows_thread_smem <= 100 * 1024;
   p->blob_bytes = smem;
   // uploads on the caller's stream (the offset tables and static inputs were produced there); one synchronisation at the end
   cudaError_t e = cudaMalloc(&p->d_row_inputs, sizeof(RowInputDev) * n_inputs);

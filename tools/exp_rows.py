@@ -32,7 +32,7 @@ for p in range(64):
         sch = infer.compiler.last_row_schedule
         temps = sum((x["out_size"] + 3) // 4 * 4 for x in sch["steps"])
         terms = sum(x["out_size"] * x["sum_card"] * len(x["in_id"]) for x in sch["steps"])
-        kern = "thread" if temps <= 64 and terms <= 320 else "warp"
+        kern = "thread" if temps <= int(os.environ.get("CBN_ROWT_MAX_TEMPS", 96)) and terms <= int(os.environ.get("CBN_ROWT_MAX_TERMS", 480)) else "warp"
         outs = [x["out_size"] for x in sch["steps"]]
         print(f"pattern {p:2d} rows   k={kk:2d} hidden/row={st.per_row_hidden:3d} steps={len(sch['steps']):3d} temps={temps:5d} madds/row={st.per_row_madds:6d} {kern:6s} {us:9.1f} us  {rows/us:8.2f} M rows/s  {st.per_row_madds*rows/us/1e3:7.1f} Gmadd/s  out_sizes={outs}")
     else:
