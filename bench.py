@@ -339,7 +339,9 @@ class Env:
         e1.record()
         torch.cuda.synchronize()
         est = self.max_over_ranks(e0.elapsed_time(e1) / 1e3 / 10)
+        margin = 1.15
         if est < 50e-6:
+            margin = 1.5          # the long graph of the timed region overlaps consecutive launches better than this short one
             # launch-latency scale: eager launches overestimate the pass; time a small graph of passes instead
             n = max(ring, 8) * 4
             g = self.graph_of([(lambda j=j: one_pass(j)) for j in range(n)])
@@ -351,7 +353,7 @@ class Env:
             torch.cuda.synchronize()
             est = min(est, self.max_over_ranks(e0.elapsed_time(e1) / 1e3 / n))
             del g
-        p = max(1, math.ceil(1.15 * min_region_s / (steps * est)))
+        p = max(1, math.ceil(margin * min_region_s / (steps * est)))
         p = min(p, 4096)
         return (p + ring - 1) // ring * ring, est
 

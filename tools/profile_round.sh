@@ -14,4 +14,6 @@ python tools/count_one.py alarm 26 3 >> $OUT/plain_count.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:count_tiles -s 2 -c 1 -o $OUT/prof_count_alarm_r2 python tools/count_one.py alarm 26 3 >> $OUT/ncu_count_r2.log 2>&1
 python tools/exp_rows_one.py 28 > $OUT/plain_rows.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:ve_rows -s 2 -c 1 -o $OUT/prof_rows28_r2 python tools/exp_rows_one.py 28 > $OUT/ncu_rows_r2.log 2>&1
+python tools/exp_rows_one.py 40 > $OUT/plain_rows40.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:ve_rows -s 2 -c 1 -o $OUT/prof_rows40_r2 python tools/exp_rows_one.py 40 > $OUT/ncu_rows40_r2.log 2>&1
 ls -la $OUT/*.ncu-rep
