@@ -154,64 +154,83 @@ def test_incremental_greedy_matches_full_rescan():
         assert not g.hidden
 
 
+def _interpret_row_schedule(sch, spec, rows):
+    """numpy interpreter of a per-row schedule (the host data ``cbn_ve_plan_create_rows`` receives), fed with the ground-truth
+    CPTs laid out as the schedule says; one posterior row per evidence row."""
+    ev_ids = sch["evidence"]
+    statics = []
+    for scope, source in zip(sch["static_scopes"], sch["static_source_scopes"]):
+        node = source[-1]        # with a table budget of one cell the static tables are the CPTs themselves
+        assert source == spec.parents[node] + [node] and sorted(scope) == sorted(source)
+        cpt = np.asarray(spec.cpts[node], dtype=np.float64).reshape([spec.cards[v] for v in source])
+        statics.append((scope, np.ascontiguousarray(cpt.transpose([source.index(v) for v in scope])).reshape(-1)))
+    got = np.zeros((rows.shape[0], spec.cards[sch["target"]]))
+    offs_all = sch["offsets"]
+    for r, ev in enumerate(rows):
+        code_of = dict(zip(ev_ids, ev))
+        bases = []
+        for scope, _ in statics:                          # slice every static table by the row's evidence codes
+            b, stride = 0, 1
+            for v in reversed(scope):
+                if v in code_of:
+                    b += int(code_of[v]) * stride
+                stride *= spec.cards[v]
+            bases.append(b)
+        temps = []
+        for st in sch["steps"]:
+            n_in, out_size = len(st["in_id"]), st["out_size"]
+            offs = offs_all[st["offsets_at"]: st["offsets_at"] + n_in * out_size].reshape(n_in, out_size).astype(np.int64)
+            out = np.zeros(out_size)
+            for sv in range(st["sum_card"]):
+                prod = np.ones(out_size)
+                for k, i in enumerate(st["in_id"]):
+                    idx = offs[k] + sv * st["sum_stride"][k]
+                    prod = prod * (statics[i][1][bases[i] + idx] if i < len(statics) else temps[i - len(statics)][idx])
+                out += prod
+            temps.append(out)
+        got[r] = temps[-1] / temps[-1].sum()
+    return got
+
+
 def test_row_schedule_interpreted_on_the_cpu_matches_the_oracle():
-    """The per-row elimination SCHEDULE (steps, offset tables, sum strides -- what ``cbn_ve_plan_create_rows`` receives) is
-    host logic: a numpy interpreter of it, fed with the ground-truth CPTs, must reproduce the oracle's posteriors.  A table
-    budget of one cell leaves every hidden variable to the per-row schedule."""
+    """The per-row elimination SCHEDULE (steps, offset tables, sum strides, the layout of every factor) is host logic: a numpy
+    interpreter of it, fed with the ground-truth CPTs, must reproduce the oracle's posteriors.  A table budget of one cell
+    leaves every hidden variable to the per-row schedule.  Checked in both layouts: every factor laid out for the step that
+    consumes it (summed variable innermost, stride 1: the contract of the executor's unrolled step bodies) and the tables' own
+    axis order (the strided bodies)."""
     import torch
 
     from oracle import cbn_oracle as O
 
-    rng = np.random.default_rng(3)
-    for spec, target, ev_names in ((synth.asia(), "lung", ["asia", "xray", "dysp"]),
-                                   (synth.random_ktree_dag(n=24, card=3, k=3, max_parents=2, seed=5), "x020", ["x003", "x011", "x017", "x023"])):
-        c = VECompiler(DryTables(spec.names, spec.cards, spec.parents_by_name()), table_budget_cells=1, row_temp_floats=1 << 22,
-                       check_support=False)
-        stats = c.compile(target, ev_names, dry=True)
-        assert stats.per_row_hidden > 0
-        sch = c.last_row_schedule
-        ev_ids = sch["evidence"]
-        assert ev_ids == [spec.names.index(e) for e in ev_names]
-        statics = []
-        n_permuted = 0
-        for scope, source in zip(sch["static_scopes"], sch["static_source_scopes"]):
-            # with a budget of 1 the static tables are the CPTs themselves, each laid out for the step that consumes it
-            # (evidence axes first, the variable that step sums over innermost)
-            node = source[-1]
-            assert source == spec.parents[node] + [node] and sorted(scope) == sorted(source)
-            cpt = np.asarray(spec.cpts[node], dtype=np.float64).reshape([spec.cards[v] for v in source])
-            statics.append((scope, np.ascontiguousarray(cpt.transpose([source.index(v) for v in scope])).reshape(-1)))
-            n_permuted += scope != source
-        assert n_permuted > 0
-        for st in sch["steps"]:                          # the layout contract of the executor's unrolled step bodies
-            assert st["sum_card"] == 1 or all(s == 1 for s in st["sum_stride"])
-        codes = synth.sample_forward_numpy(spec, 9, 0, 40)
-        rows = codes[ev_ids].T
-        got = np.zeros((rows.shape[0], spec.cards[sch["target"]]))
-        offs_all = sch["offsets"]
-        for r, ev in enumerate(rows):
-            code_of = dict(zip(ev_ids, ev))
-            bases = []
-            for scope, _ in statics:                      # slice every static table by the row's evidence codes
-                b, stride = 0, 1
-                for v in reversed(scope):
-                    if v in code_of:
-                        b += int(code_of[v]) * stride
-                    stride *= spec.cards[v]
-                bases.append(b)
-            temps = []
-            for st in sch["steps"]:
-                n_in, out_size = len(st["in_id"]), st["out_size"]
-                offs = offs_all[st["offsets_at"]: st["offsets_at"] + n_in * out_size].reshape(n_in, out_size)
-                out = np.zeros(out_size)
-                for o in range(out_size):
-                    for sv in range(st["sum_card"]):
-                        prod = 1.0
-                        for k, i in enumerate(st["in_id"]):
-                            idx = int(offs[k, o]) + sv * st["sum_stride"][k]
-                            prod *= statics[i][1][bases[i] + idx] if i < len(statics) else temps[i - len(statics)][idx]
-                        out[o] += prod
-                temps.append(out)
-            got[r] = temps[-1] / temps[-1].sum()
-        want = O.ve_posterior(O.DiscreteNet(spec.cards, spec.parents, spec.cpts), sch["target"], ev_ids, rows, dtype=torch.float64)
-        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
+    small_layers = synth.layered_dag(layers=4, width=6, seed=21)          # cards 2..8: odd and even run lengths
+    cases = ((synth.asia(), "lung", ["asia", "xray", "dysp"]),
+             (synth.random_ktree_dag(n=24, card=3, k=3, max_parents=2, seed=5), "x020", ["x003", "x011", "x017", "x023"]),
+             (small_layers, "l01_02", ["l03_00", "l03_03", "l03_05", "l02_01", "l00_04"]),
+             (small_layers, "l03_04", ["l00_00", "l00_03", "l01_05", "l02_02"]))
+    for spec, target, ev_names in cases:
+        for unit in (True, False):
+            c = VECompiler(DryTables(spec.names, spec.cards, spec.parents_by_name()), table_budget_cells=1, row_temp_floats=1 << 22,
+                           check_support=False, row_unit_layout=unit)
+            stats = c.compile(target, ev_names, dry=True)
+            assert stats.per_row_hidden > 0
+            sch = c.last_row_schedule
+            ev_ids = sch["evidence"]
+            assert ev_ids == [spec.names.index(e) for e in ev_names]
+            sums = [st for st in sch["steps"] if st["sum_card"] > 1]
+            n_permuted = sum(a != b for a, b in zip(sch["static_scopes"], sch["static_source_scopes"]))
+            if unit:
+                assert all(s == 1 for st in sums for s in st["sum_stride"]) and n_permuted > 0
+                for scope in sch["static_scopes"]:         # evidence axes first, so a row's slice stays contiguous
+                    is_ev = [v in ev_ids for v in scope]
+                    assert is_ev == sorted(is_ev, reverse=True)
+            else:
+                assert n_permuted == 0 and any(s != 1 for st in sums for s in st["sum_stride"])
+            # every factor is consumed exactly once, and never before it exists
+            used = [i for st in sch["steps"] for i in st["in_id"]]
+            assert sorted(used) == list(range(len(sch["static_scopes"]) + len(sch["steps"]) - 1))
+            assert all(i < len(sch["static_scopes"]) + j for j, st in enumerate(sch["steps"]) for i in st["in_id"])
+            codes = synth.sample_forward_numpy(spec, 9, 0, 40)
+            rows = codes[ev_ids].T
+            got = _interpret_row_schedule(sch, spec, rows)
+            want = O.ve_posterior(O.DiscreteNet(spec.cards, spec.parents, spec.cpts), sch["target"], ev_ids, rows, dtype=torch.float64)
+            np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15)
