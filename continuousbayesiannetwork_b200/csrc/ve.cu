@@ -1214,6 +1214,9 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   // three stages: deeper prefetch only takes shared memory away from L1, which tracks the outstanding table gathers
   // (measured on B200: 4+ stages are slower)
   int n_stages = 3;
+  static int stages_env = -1;
+  if (stages_env < 0) { const char* e = getenv("CBN_GATHER_STAGES"); stages_env = e ? atoi(e) : 0; }
+  if (stages_env >= 2 && stages_env <= GT_MAX_STAGES) n_stages = stages_env;
   while (n_stages > 2 && blob_pad + n_stages * stage_bytes > 56 * 1024) --n_stages;
   const int hints = 7;     // evict-first for the code and posterior streams, evict-last for the table
   const size_t smem = blob_pad + n_stages * stage_bytes;
