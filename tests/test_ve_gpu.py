@@ -683,6 +683,13 @@ def test_per_row_executor_matches_oracle():
             cols[3][5] = 1234.0
             got32 = plan.run_f32(cols, ev.shape[0]).cpu().numpy()
             assert np.array_equal(got32, got)
+    # the schedule is host data that the library range-checks: an offset that leaves its factor is refused at plan creation
+    sch = infer.compiler.last_row_schedule
+    for bad_value in (-1, 1 << 28):
+        bad = plan.offsets.copy()
+        bad[len(bad) // 2] = bad_value
+        with pytest.raises(ValueError, match="leaves the factor"):
+            RowPlan(t, plan.target, plan.evidence, plan.card_t, plan.inputs, sch["steps"], bad, plan.stats, plan.log_space)
     # naive-Bayes shape: one hidden cause with many observed children: the boundary (3^40 / 3^24) cannot be tabulated.
     # 40 children -> warp-per-row kernel, 24 children -> a short schedule, the one-thread-per-row kernel; both arithmetic modes
     for n_child in (40, 24):
