@@ -16,6 +16,15 @@ ids = [spec.names.index(e) for e in synth.ALARM_EVIDENCE]
 full = sample_network(spec, seed=1236, first=0, n=rows, device=dev, tables=tables)
 ev = full[ids].contiguous()
 del full
+if os.environ.get("MAP_UNIFORM"):      # evidence drawn uniformly instead of from the network: no hot configurations
+    g = torch.Generator(device=dev).manual_seed(5)
+    for j, i in enumerate(ids):
+        ev[j] = torch.randint(0, spec.cards[i], (ev.shape[1],), generator=g, device=dev, dtype=torch.uint8)
+if os.environ.get("MAP_SORTED"):       # rows sorted by configuration: neighbouring rows share table sectors
+    key = torch.zeros(ev.shape[1], dtype=torch.int64, device=dev)
+    for j, i in enumerate(ids):
+        key = key * spec.cards[i] + ev[j].long()
+    ev = ev[:, torch.argsort(key)].contiguous()
 plan = infer.plan(synth.ALARM_TARGETS[0], synth.ALARM_EVIDENCE)
 plan.set_static_evidence(True)
 out = torch.empty(rows, dtype=torch.float32, device=dev)
