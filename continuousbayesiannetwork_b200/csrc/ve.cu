@@ -753,7 +753,12 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned
 // The evidence columns a plan reads are brought into shared memory by 1-D bulk async copies (TMA engine), one
 // 1024-row tile per stage, GT_STAGES tiles ahead: a thread never waits on DRAM for its codes, so the only exposed
 // latency left is the table gather itself, and the copies keep far more bytes in flight than register loads can.
-constexpr int GT_TILE_ROWS = 4 * GATHER_TPB;    // one quad per thread per tile
+// quads per thread and tile: one for the generic table list (more, smaller tiles keep more gathers in flight: MAP and the
+// 200-node patterns lose 25-30 % with two), two for the interleaved multi-target table, whose 32-byte gathers and stores
+// leave the per-tile synchronisation as the larger share (measured: +2 % on the headline)
+__host__ __device__ constexpr int gt_qpt(int nout) { return nout >= 2 ? 2 : 1; }
+__host__ __device__ constexpr int gt_tile_rows(int nout) { return 4 * GATHER_TPB * gt_qpt(nout); }
+constexpr int GT_TILE_ROWS_MAX = gt_tile_rows(2);
 constexpr int GT_MAX_COLS = 16;
 constexpr int GT_MAX_STAGES = 4;
 
@@ -761,11 +766,12 @@ struct TileCols {
   int n;
   uint8_t slot[GT_MAX_COLS];     // evidence slot staged as tile column c
 };
+template <int TILE_ROWS>
 struct TileLoader {
-  const unsigned char* stage;    // [n cols][GT_TILE_ROWS] codes of the current tile; descriptors hold tile columns, not slots
+  const unsigned char* stage;    // [n cols][TILE_ROWS] codes of the current tile; descriptors hold tile columns, not slots
   int64_t quad0;
   __device__ __forceinline__ uint32_t load4(int col, int64_t quad) const {
-    return *reinterpret_cast<const uint32_t*>(stage + col * GT_TILE_ROWS + (int(quad - quad0) << 2));
+    return *reinterpret_cast<const uint32_t*>(stage + col * TILE_ROWS + (int(quad - quad0) << 2));
   }
 };
 
@@ -774,6 +780,7 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned
                                                                   int desc_bytes, int n_tables, const __grid_constant__ TileCols cols,
                                                                   int n_stages, int hints, const uint8_t* __restrict__ ev, int64_t ld,
                                                                   int64_t n_rows, int early_ev, const __grid_constant__ GatherOuts outs) {
+  constexpr int GT_TILE_ROWS = gt_tile_rows(NOUT), GT_QPT = gt_qpt(NOUT);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
   pdl_trigger();
@@ -836,15 +843,18 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned
     mbar_wait(&full[s], round & 1u);
     const int64_t tile = int64_t(blockIdx.x) + i * gridDim.x;
     const int64_t q0 = tile * (GT_TILE_ROWS / 4);
-    const int64_t q = q0 + threadIdx.x;
-    TileLoader L{stages + size_t(s) * stage_bytes, q0};
-    if (q < nquads) {
-      if constexpr (NOUT >= 2) {
-        const GTable& T = st[0];
-        const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
-        gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs, st_pol, ld_pol);
-      } else {
-        gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs, st_pol, ld_pol);
+    TileLoader<GT_TILE_ROWS> L{stages + size_t(s) * stage_bytes, q0};
+#pragma unroll 1
+    for (int qq = 0; qq < GT_QPT; ++qq) {
+      const int64_t q = q0 + qq * GATHER_TPB + threadIdx.x;
+      if (q < nquads) {
+        if constexpr (NOUT >= 2) {
+          const GTable& T = st[0];
+          const float* base = T.smem_off >= 0 ? pool + T.smem_off : T.data;
+          gather_inter_rows4<CT, NOUT>(T, base, L, q, n_rows, outs, st_pol, ld_pol);
+        } else {
+          gather_rows4<CT>(st, n_tables, pool, L, q, n_rows, outs, st_pol, ld_pol);
+        }
       }
     }
     __syncwarp();
@@ -1208,6 +1218,7 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
       while (c < cols.n && cols.slot[c] != t.slot[j]) ++c;
       if (c == cols.n) cols.slot[cols.n++] = t.slot[j];
     }
+  constexpr int GT_TILE_ROWS = gt_tile_rows(NOUT);
   const size_t blob_pad = (p->blob_bytes + 127) & ~size_t(127);
   const size_t stage_bytes = size_t(cols.n) * GT_TILE_ROWS;
   // as many stages as the shared memory of one SM allows at the occupancy the registers were bounded for
@@ -1249,7 +1260,7 @@ bool use_tiles(const cbn_ve_plan* p, int64_t n_rows, bool force = false) {
     for (int j = 0; j < t.n_ev; ++j)
       if (!seen[t.slot[j]]) { seen[t.slot[j]] = 1; ++n; }
   if (n < 1 || n > GT_MAX_COLS) return false;
-  if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS > 150 * 1024) return false;
+  if (((p->blob_bytes + 127) & ~size_t(127)) + 2 * size_t(n) * GT_TILE_ROWS_MAX > 150 * 1024) return false;
   // large tables in global memory (not staged): the tile-staged kernel carries the L2 policies that keep the table
   // resident while the streams pass through, which pays from a few hundred thousand rows on
   if (!p->staged && p->table_bytes >= (4ll << 20) && n_rows >= (int64_t(1) << 18)) return true;
