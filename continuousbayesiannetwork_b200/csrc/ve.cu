@@ -753,12 +753,12 @@ __global__ void __launch_bounds__(GATHER_TPB) gather_inter_kernel(const unsigned
 // The evidence columns a plan reads are brought into shared memory by 1-D bulk async copies (TMA engine), one
 // 1024-row tile per stage, GT_STAGES tiles ahead: a thread never waits on DRAM for its codes, so the only exposed
 // latency left is the table gather itself, and the copies keep far more bytes in flight than register loads can.
-// quads per thread and tile: one for the generic table list (more, smaller tiles keep more gathers in flight: MAP and the
-// 200-node patterns lose 25-30 % with two), two for the interleaved multi-target table, whose 32-byte gathers and stores
-// leave the per-tile synchronisation as the larger share (measured: +2 % on the headline)
-__host__ __device__ constexpr int gt_qpt(int nout) { return nout >= 2 ? 2 : 1; }
-__host__ __device__ constexpr int gt_tile_rows(int nout) { return 4 * GATHER_TPB * gt_qpt(nout); }
-constexpr int GT_TILE_ROWS_MAX = gt_tile_rows(2);
+// quads per thread and tile (QPT).  One for the generic table list (more, smaller tiles keep more gathers in flight: MAP
+// and the 200-node patterns lose 25-30 % with two).  The interleaved multi-target table runs two when the batch gives
+// every CTA enough tiles to reach a steady state (the headline's 16M rows: 0.750 -> 0.768 of the HBM peak) and one
+// otherwise (2M rows per GPU at N=8: two would cost 10 %)
+constexpr int GT_MAX_QPT = 2;
+constexpr int GT_TILE_ROWS_MAX = 4 * GATHER_TPB * GT_MAX_QPT;
 constexpr int GT_MAX_COLS = 16;
 constexpr int GT_MAX_STAGES = 4;
 
@@ -775,12 +775,12 @@ struct TileLoader {
   }
 };
 
-template <int CT, int NOUT>     // NOUT == 0: generic table list (gather_rows4); NOUT >= 2: one interleaved table
+template <int CT, int NOUT, int GT_QPT>     // NOUT == 0: generic table list (gather_rows4); NOUT >= 2: one interleaved table
 __global__ void __launch_bounds__(GATHER_TPB) gather_tiles_kernel(const unsigned char* __restrict__ blob, int blob_bytes,
                                                                   int desc_bytes, int n_tables, const __grid_constant__ TileCols cols,
                                                                   int n_stages, int hints, const uint8_t* __restrict__ ev, int64_t ld,
                                                                   int64_t n_rows, int early_ev, const __grid_constant__ GatherOuts outs) {
-  constexpr int GT_TILE_ROWS = gt_tile_rows(NOUT), GT_QPT = gt_qpt(NOUT);
+  constexpr int GT_TILE_ROWS = 4 * GATHER_TPB * GT_QPT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
   pdl_trigger();
@@ -1208,9 +1208,9 @@ int launch_inter(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
 }
 
 // tile-staged launch: persistent CTAs, as many as fit per SM for this plan's shared-memory footprint
-template <int CT, int NOUT>
-int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
-                 cudaStream_t s) {
+template <int CT, int NOUT, int QPT>
+int launch_tiles_q(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
+                   cudaStream_t s) {
   TileCols cols{};
   for (const GTable& t : p->h_tables)
     for (int j = 0; j < t.n_ev; ++j) {
@@ -1218,7 +1218,7 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
       while (c < cols.n && cols.slot[c] != t.slot[j]) ++c;
       if (c == cols.n) cols.slot[cols.n++] = t.slot[j];
     }
-  constexpr int GT_TILE_ROWS = gt_tile_rows(NOUT);
+  constexpr int GT_TILE_ROWS = 4 * GATHER_TPB * QPT;
   const size_t blob_pad = (p->blob_bytes + 127) & ~size_t(127);
   const size_t stage_bytes = size_t(cols.n) * GT_TILE_ROWS;
   // as many stages as the shared memory of one SM allows at the occupancy the registers were bounded for
@@ -1233,20 +1233,35 @@ int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t 
   const size_t smem = blob_pad + n_stages * stage_bytes;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_tiles_kernel<CT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CBN_CUDA(ctx, cudaFuncSetAttribute(gather_tiles_kernel<CT, NOUT, QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[ctx->device & 63] = true;
   }
   if (p->occ[1] == 0 || p->occ_smem[1] != smem) {
     int occ = 1;
-    CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_tiles_kernel<CT, NOUT>, GATHER_TPB, smem));
+    CBN_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_tiles_kernel<CT, NOUT, QPT>, GATHER_TPB, smem));
     p->occ[1] = std::max(occ, 1); p->occ_smem[1] = smem;
   }
   const int64_t n_tiles = (n_rows + GT_TILE_ROWS - 1) / GT_TILE_ROWS;
   const int per_sm = p->occ[1];
   const int blocks = (int)balanced_grid(n_tiles, int64_t(ctx->sm_count) * per_sm);
-  CBN_CUDA(ctx, launch_pdl(gather_tiles_kernel<CT, NOUT>, blocks, GATHER_TPB, smem, s, p->d_blob, (int)p->blob_bytes,
+  CBN_CUDA(ctx, launch_pdl(gather_tiles_kernel<CT, NOUT, QPT>, blocks, GATHER_TPB, smem, s, p->d_blob, (int)p->blob_bytes,
                            (int)p->desc_bytes, p->n_tables, cols, n_stages, hints, ev, ld, n_rows, p->static_evidence, outs));
   return CBN_OK;
+}
+
+template <int CT, int NOUT>
+int launch_tiles(cbn_ctx* ctx, const cbn_ve_plan* p, const uint8_t* ev, int64_t ld, int64_t n_rows, const GatherOuts& outs,
+                 cudaStream_t s) {
+  if constexpr (NOUT >= 2) {
+    // two quads per thread and tile once every resident CTA gets at least ten such tiles (measured: 16.8M rows +2.4 %,
+    // 8.4M rows -1 %, 2.1M rows -10 %; CBN_GATHER_QPT=1|2 forces it)
+    static int qpt_env = -1;
+    if (qpt_env < 0) { const char* e = getenv("CBN_GATHER_QPT"); qpt_env = e ? atoi(e) : 0; }
+    const int64_t big_tiles = n_rows / (4 * GATHER_TPB * GT_MAX_QPT);
+    const bool two = qpt_env ? qpt_env == 2 : big_tiles >= int64_t(ctx->sm_count) * 4 * 10;
+    if (two) return launch_tiles_q<CT, NOUT, 2>(ctx, p, ev, ld, n_rows, outs, s);
+  }
+  return launch_tiles_q<CT, NOUT, 1>(ctx, p, ev, ld, n_rows, outs, s);
 }
 
 // large batches go through the tile-staged kernel (CBN_GATHER_TILES=0/1 forces the choice; default: >= 2^21 rows)
