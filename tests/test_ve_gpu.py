@@ -648,6 +648,20 @@ def test_tile_staged_kernel_matches_direct_kernel_on_large_batches():
     ok = np.ones(600, bool); ok[600 - 2] = False
     want = O.ve_posterior(net, spec.names.index("VENTLUNG"), ids, ev[-600:][ok])
     np.testing.assert_allclose(got[ok], want, rtol=RTOL, atol=1e-30)
+    # from ten 2048-row tiles per resident CTA on, the interleaved multi-target table runs two quads per thread and tile:
+    # a ragged batch of that size (the rows above, repeated) against the same rows in 1M-row calls of the direct kernel
+    reps = 3
+    n2 = reps * n - 517
+    m2 = _codes_matrix(np.concatenate([ev] * reps)[:n2])
+    fused = infer.fused_plan(synth.ALARM_TARGETS, synth.ALARM_EVIDENCE)
+    assert n2 // 2048 >= torch.cuda.get_device_properties(0).multi_processor_count * 40
+    big = fused.run_codes(m2, n2)
+    for s0 in range(0, n2, half):
+        cnt = min(half, n2 - s0)
+        for o, q in zip(big, fused.run_codes(m2[:, s0:], cnt)):
+            assert torch.equal(o[s0:s0 + cnt], q)
+    for o in big:
+        assert bool((o[12345] == 0).all()) and bool((o[n + 12345] == 0).all()) and bool((o[n + n - 2] == 0).all())
 
 
 def test_per_row_executor_matches_oracle():
