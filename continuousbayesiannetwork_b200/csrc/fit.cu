@@ -137,6 +137,22 @@ __device__ __forceinline__ bool domain_note(uint32_t* sset, float x, Recent& r, 
   return true;
 }
 
+struct Noted { Recent r; bool ok; };
+__device__ __noinline__ Noted domain_note8(uint32_t* sset, float4 a, float4 c, Recent r, int* overflow) {
+  const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  bool ok = true;
+#pragma unroll 1
+  for (int k = 0; k < 8 && ok; ++k) ok = domain_note(sset, v[k], r, overflow);      // rare path: kept small, not fast
+  return Noted{r, ok};
+}
+__device__ __forceinline__ bool recent_has(uint32_t raw, const Recent& r) {
+  return (raw == r.v0) | (raw == r.v1) | (raw == r.v2) | (raw == r.v3);
+}
+__device__ __forceinline__ bool recent_all(const float4& v, const Recent& r) {
+  return recent_has(__float_as_uint(v.x), r) & recent_has(__float_as_uint(v.y), r) & recent_has(__float_as_uint(v.z), r) &
+         recent_has(__float_as_uint(v.w), r);
+}
+
 // 128-bit loads, eight values per thread and iteration (the column base is 16-byte aligned when VEC)
 template <bool VEC>
 __global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant__ ColPtrs cols, int64_t n, uint32_t* gset_all) {
@@ -154,14 +170,31 @@ __global__ void __launch_bounds__(256) domain_scan_kernel(const __grid_constant_
   if (threadIdx.x == 0) ok = set_insert(sset, canon_bits(first));
   if (VEC) {
     const int64_t n4 = n >> 2;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4 && ok; i += 2 * stride) {
-      const float4 a = ld_nc_f128(reinterpret_cast<const float4*>(col) + i);
-      const bool two = i + stride < n4;
-      float4 c = a;
-      if (two) c = ld_nc_f128(reinterpret_cast<const float4*>(col) + i + stride);
-      ok = domain_note(sset, a.x, r, overflow) && domain_note(sset, a.y, r, overflow) && domain_note(sset, a.z, r, overflow) &&
-           domain_note(sset, a.w, r, overflow) && domain_note(sset, c.x, r, overflow) && domain_note(sset, c.y, r, overflow) &&
-           domain_note(sset, c.z, r, overflow) && domain_note(sset, c.w, r, overflow);
+    const float4* __restrict__ col4 = reinterpret_cast<const float4*>(col);
+    // software-pipelined: the loads of the next iteration are issued before the eight values of this one are looked at
+    // (the look-ups branch and carry `ok`, so the compiler cannot hoist the loads itself)
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool have = i < n4;
+    float4 a = make_float4(first, first, first, first), c = a;
+    if (have) {
+      a = ld_nc_f128(col4 + i);
+      c = i + stride < n4 ? ld_nc_f128(col4 + i + stride) : a;
+    }
+    while (have && ok) {
+      const int64_t ni = i + 2 * stride;
+      const bool nh = ni < n4;
+      float4 na = a, nc = c;
+      if (nh) {
+        na = ld_nc_f128(col4 + ni);
+        nc = ni + stride < n4 ? ld_nc_f128(col4 + ni + stride) : na;
+      }
+      // straight-line test of all eight values against the register cache; only a miss takes the per-value path, which is
+      // an out-of-line call so that the streaming loop stays at a few dozen registers (eight CTAs per SM)
+      if (!(recent_all(a, r) & recent_all(c, r))) {
+        const Noted t = domain_note8(sset, a, c, r, overflow);
+        r = t.r; ok = t.ok;
+      }
+      a = na; c = nc; i = ni; have = nh;
     }
     for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n && ok; i += stride)
       ok = domain_note(sset, __ldg(col + i), r, overflow);
@@ -235,8 +268,13 @@ extern "C" int cbn_domain_f32_multi(cbn_ctx* ctx, const float* const* cols, int3
     CBN_CUDA(ctx, cbn_scratch_alloc(ctx, (void**)&gset, size_t(nc) * (DOM_SLOTS + 1) * sizeof(uint32_t), s));
     domain_init_kernel<<<nc, 256, 0, s>>>(gset);
     if (n > 0) {
-      // enough CTAs to fill the machine across all columns of the launch
-      int bx = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), std::max(1, (ctx->sm_count * 8 + nc - 1) / nc));
+      // exactly one wave of resident CTAs across all columns of the launch (grid-stride inside: a partial second wave
+      // would leave most of the machine idle for a third of the run)
+      int occ = 4;
+      if (aligned) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, domain_scan_kernel<true>, 256, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, domain_scan_kernel<false>, 256, 0);
+      const int slots = ctx->sm_count * std::max(occ, 1);
+      int bx = (int)std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), std::max(1, slots / nc));
       dim3 grid(std::max(bx, 1), nc);
       if (aligned) domain_scan_kernel<true><<<grid, 256, 0, s>>>(cp, n, gset);
       else domain_scan_kernel<false><<<grid, 256, 0, s>>>(cp, n, gset);
